@@ -1,0 +1,435 @@
+// csr5_capi.cu -- handle state machine and the extern "C" ABI of libcsr5_b200.so
+// (include/csr5_b200.h).  Mirrors anonymouslibHandle<int, unsigned int, VT>
+// (CSR5_cuda/anonymouslib_cuda.h:11-318): CSR arrays are borrowed, the five CSR5 arrays are owned,
+// col/val are permuted in place between asCSR5() and asCSR().
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "csr5_internal.h"
+
+using namespace csr5;
+
+struct csr5b200_handle_s {
+    Plan pl;
+    SpmvTuning tune;
+    int format = -1;          // the reference leaves _format unset until inputCSR
+    cudaStream_t stream = 0;  // legacy default stream, like the reference
+    int ignore_alpha = 0;
+    int last_cuda_error = 0;
+    int kernel_in_use = 0;
+    int launches_per_spmv = 0;
+    void *x_stage = nullptr;  // device staging for spmv_host
+    void *y_stage = nullptr;
+    int kernel_timing = 0;
+    std::vector<cudaEvent_t> ev;  // begin/end pairs of the timed main kernels
+    size_t ev_used = 0;           // events recorded since the last get_kernel_times()
+};
+
+namespace {
+
+int cuda_fail(csr5b200_handle_t h, cudaError_t e)
+{
+    if (h) h->last_cuda_error = (int)e;
+    return CSR5B200_CUDA_ERROR;
+}
+
+#define CU(h, call)                                        \
+    do {                                                   \
+        cudaError_t e__ = (call);                          \
+        if (e__ != cudaSuccess) return cuda_fail(h, e__);  \
+    } while (0)
+
+void release_csr5_arrays(csr5b200_handle_t h)
+{
+    Plan &pl = h->pl;
+    cudaFree(pl.tile_ptr);
+    cudaFree(pl.desc);
+    cudaFree(pl.desc_off_ptr);
+    cudaFree(pl.desc_off);
+    cudaFree(pl.calibrator);
+    cudaFree(pl.dev_flags);
+    pl.tile_ptr = nullptr;
+    pl.desc = nullptr;
+    pl.desc_off_ptr = nullptr;
+    pl.desc_off = nullptr;
+    pl.calibrator = nullptr;
+    pl.dev_flags = nullptr;
+}
+
+// anonymouslib_cuda.h:294-318 -- r / s / t / u = 4 / 32 / 256 / 6 on k = nnz / m
+constexpr size_t MAX_TIMED_SPMV = 4096;
+
+int auto_sigma(int m, int nnz)
+{
+    const int k = m > 0 ? nnz / m : 0;
+    if (k <= 4) return 4;
+    if (k <= 32) return k;
+    if (k <= 256) return 32;
+    return 6;
+}
+
+}  // namespace
+
+extern "C" {
+
+int csr5b200_create(int m, int n, int value_bytes, csr5b200_handle_t *out)
+{
+    if (!out || m < 0 || n < 0) return CSR5B200_INVALID_ARGUMENT;
+    if (value_bytes != 4 && value_bytes != 8) return CSR5B200_UNSUPPORTED_VALUE_TYPE;
+    csr5b200_handle_t h = new (std::nothrow) csr5b200_handle_s();
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    h->pl.m = m;
+    h->pl.n = n;
+    h->pl.value_bytes = value_bytes;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        h->tune.num_sms = sms;
+    *out = h;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_warmup(csr5b200_handle_t h)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    CU(h, launch_warmup(h->stream));
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_input_csr(csr5b200_handle_t h, int nnz, int *row_ptr, int *col, void *val)
+{
+    if (!h || nnz < 0) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format == CSR5B200_FORMAT_CSR5) {  // the reference would leak; restore first
+        const int err = csr5b200_as_csr(h);
+        if (err) return err;
+    }
+    h->format = CSR5B200_FORMAT_CSR;
+    h->pl.nnz = nnz;
+    h->pl.row_ptr = row_ptr;
+    h->pl.col = col;
+    h->pl.val = val;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_set_x(csr5b200_handle_t h, void *x)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    h->pl.x = x;  // no texture object: sm_100a gathers through the read-only LDG path
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_set_sigma(csr5b200_handle_t h, int sigma)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    h->pl.sigma = sigma == CSR5B200_AUTO_TUNED_SIGMA ? auto_sigma(h->pl.m, h->pl.nnz) : sigma;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    switch (option) {
+        case CSR5B200_OPT_KERNEL:
+            if (value < 0 || value > 2) return CSR5B200_INVALID_ARGUMENT;
+            h->tune.kernel = value;
+            break;
+        case CSR5B200_OPT_IGNORE_ALPHA: h->ignore_alpha = value != 0; break;
+        case CSR5B200_OPT_TMA_STAGES: h->tune.tma_stages = value; break;
+        case CSR5B200_OPT_TMA_WARPS: h->tune.tma_warps = value; break;
+        case CSR5B200_OPT_CTAS_PER_SM: h->tune.ctas_per_sm = value; break;
+        case CSR5B200_OPT_KERNEL_TIMING: h->kernel_timing = value != 0; break;
+        default: return CSR5B200_INVALID_ARGUMENT;
+    }
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_as_csr5(csr5b200_handle_t h)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format == CSR5B200_FORMAT_CSR5) return CSR5B200_SUCCESS;
+    if (h->format != CSR5B200_FORMAT_CSR) return CSR5B200_UNKNOWN_FORMAT;
+    Plan &pl = h->pl;
+    if (pl.sigma < SIGMA_MIN || pl.sigma > SIGMA_MAX) return CSR5B200_CSR_TO_CSR5_FAILED;
+
+    // anonymouslib_cuda.h:121-137
+    int base = 2;
+    pl.bit_y = 1;
+    while (base < OMEGA * pl.sigma) { base *= 2; pl.bit_y++; }
+    base = 2;
+    pl.bit_ss = 1;
+    while (base < OMEGA) { base *= 2; pl.bit_ss++; }
+    if (pl.bit_y + pl.bit_ss > 31) return CSR5B200_UNSUPPORTED_CSR5_OMEGA;
+    pl.num_packet = (pl.bit_y + pl.bit_ss + pl.sigma + 31) / 32;
+    const long long tile = (long long)OMEGA * pl.sigma;
+    pl.p = (int)((pl.nnz + tile - 1) / tile);
+    pl.tail_start = 0;
+    pl.num_offsets = 0;
+    pl.needs_zero_fill = 0;
+
+    if (pl.p == 0) {  // empty matrix: spmv() only clears y
+        h->format = CSR5B200_FORMAT_CSR5;
+        return CSR5B200_SUCCESS;
+    }
+
+    const size_t vb = (size_t)pl.value_bytes;
+    void *scan_scratch = nullptr;
+    const size_t scan_bytes = scan_scratch_bytes(pl.p);
+    auto fail = [&](cudaError_t e) {
+        cudaFree(scan_scratch);
+        release_csr5_arrays(h);
+        return cuda_fail(h, e);
+    };
+#define CUF(call)                                   \
+    do {                                            \
+        cudaError_t e__ = (call);                   \
+        if (e__ != cudaSuccess) return fail(e__);   \
+    } while (0)
+
+    CUF(cudaMalloc(&pl.tile_ptr, (size_t)(pl.p + 1) * sizeof(uint32_t)));
+    CUF(cudaMalloc(&pl.desc, (size_t)pl.p * OMEGA * pl.num_packet * sizeof(uint32_t)));
+    CUF(cudaMalloc(&pl.desc_off_ptr, (size_t)(pl.p + 1) * sizeof(int)));
+    CUF(cudaMalloc(&pl.calibrator, (size_t)pl.p * vb));
+    CUF(cudaMalloc(&pl.dev_flags, 8 * sizeof(int)));
+    CUF(cudaMalloc(&scan_scratch, scan_bytes));
+    CUF(cudaMemsetAsync(pl.dev_flags, 0, 8 * sizeof(int), h->stream));
+    CUF(cudaMemsetAsync(pl.calibrator, 0, (size_t)pl.p * vb, h->stream));
+
+    CUF(launch_tile_ptr(pl, h->stream));
+    CUF(launch_tile_desc(pl, h->stream));
+    CUF(launch_scan_offsets(pl, scan_scratch, scan_bytes, h->stream));
+
+    // One blocking read-back (the reference does three, anonymouslib_cuda.h:166, format_cuda.h:331,342):
+    // tail start, first tile's row, number of empty-row table entries, "any dirty tile" flag.
+    uint32_t tp_last = 0, tp_first = 0;
+    int num_offsets = 0, any_dirty = 0;
+    CUF(cudaMemcpyAsync(&tp_last, pl.tile_ptr + pl.p - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUF(cudaMemcpyAsync(&tp_first, pl.tile_ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUF(cudaMemcpyAsync(&num_offsets, pl.desc_off_ptr + pl.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUF(cudaMemcpyAsync(&any_dirty, pl.dev_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUF(cudaStreamSynchronize(h->stream));
+    pl.tail_start = (int)(tp_last & ROW_MASK);
+    pl.num_offsets = num_offsets;
+    // Rows that no tile stores: empty rows inside CSR5 tiles and the empty rows in front of the
+    // first non-empty row.  (Empty rows of the tail are written by the tail warps.)
+    pl.needs_zero_fill = (any_dirty || (tp_first & ROW_MASK) > 0) ? 1 : 0;
+
+    if (num_offsets > 0) {
+        CUF(cudaMalloc(&pl.desc_off, (size_t)num_offsets * sizeof(int)));
+        CUF(launch_desc_offset(pl, h->stream));
+    }
+    CUF(launch_transpose(pl, true, h->stream));
+    CUF(cudaStreamSynchronize(h->stream));
+    cudaFree(scan_scratch);
+#undef CUF
+    h->format = CSR5B200_FORMAT_CSR5;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_as_csr(csr5b200_handle_t h)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_SUCCESS;
+    if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
+    if (h->pl.p > 0) {
+        CU(h, launch_transpose(h->pl, false, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    release_csr5_arrays(h);
+    h->format = CSR5B200_FORMAT_CSR;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_UNSUPPORTED_CSR_SPMV;
+    if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
+    if (!y || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
+    if (h->ignore_alpha) alpha = 1.0;
+    cudaError_t e;
+    h->tune.ev_begin = h->tune.ev_end = nullptr;
+    if (h->kernel_timing && h->ev_used + 2 <= 2 * MAX_TIMED_SPMV) {
+        while (h->ev.size() < h->ev_used + 2) {
+            cudaEvent_t ev;
+            CU(h, cudaEventCreate(&ev));
+            h->ev.push_back(ev);
+        }
+        h->tune.ev_begin = h->ev[h->ev_used];
+        h->tune.ev_end = h->ev[h->ev_used + 1];
+        h->ev_used += 2;
+    }
+    if (h->pl.value_bytes == 8)
+        e = launch_spmv_f64(h->pl, h->tune, alpha, static_cast<double *>(y), h->stream, &h->kernel_in_use,
+                            &h->launches_per_spmv);
+    else
+        e = launch_spmv_f32(h->pl, h->tune, (float)alpha, static_cast<float *>(y), h->stream,
+                            &h->kernel_in_use, &h->launches_per_spmv);
+    if (e != cudaSuccess) return cuda_fail(h, e);
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_destroy(csr5b200_handle_t h)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    int err = CSR5B200_SUCCESS;
+    if (h->format == CSR5B200_FORMAT_CSR5) err = csr5b200_as_csr(h);
+    cudaFree(h->x_stage);
+    cudaFree(h->y_stage);
+    h->x_stage = h->y_stage = nullptr;
+    for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
+    h->ev.clear();
+    h->ev_used = 0;
+    return err;
+}
+
+int csr5b200_free(csr5b200_handle_t h)
+{
+    if (!h) return CSR5B200_SUCCESS;
+    const int err = csr5b200_destroy(h);
+    delete h;
+    return err;
+}
+
+int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out)
+{
+    if (!h || !out) return CSR5B200_INVALID_ARGUMENT;
+    const Plan &pl = h->pl;
+    std::memset(out, 0, sizeof(*out));
+    out->format = h->format;
+    out->m = pl.m;
+    out->n = pl.n;
+    out->nnz = pl.nnz;
+    out->value_bytes = pl.value_bytes;
+    out->sigma = pl.sigma;
+    out->bit_y_offset = pl.bit_y;
+    out->bit_scansum_offset = pl.bit_ss;
+    out->num_packet = pl.num_packet;
+    out->p = pl.p;
+    out->num_offsets = pl.num_offsets;
+    out->tail_partition_start = pl.tail_start;
+    out->needs_zero_fill = pl.needs_zero_fill;
+    out->kernel_in_use = h->kernel_in_use;
+    out->partition_pointer = pl.tile_ptr;
+    out->partition_descriptor = pl.desc;
+    out->partition_descriptor_offset_pointer = pl.desc_off_ptr;
+    out->partition_descriptor_offset = pl.desc_off;
+    out->calibrator = pl.calibrator;
+    out->last_cuda_error = h->last_cuda_error;
+    out->launches_per_spmv = h->launches_per_spmv;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_get_kernel_times(csr5b200_handle_t h, float *ms, int capacity, int *count)
+{
+    if (!h || !count || (capacity > 0 && !ms)) return CSR5B200_INVALID_ARGUMENT;
+    *count = 0;
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i + 1 < h->ev_used && *count < capacity; i += 2) {
+        CU(h, cudaEventElapsedTime(ms + *count, h->ev[i], h->ev[i + 1]));
+        ++*count;
+    }
+    h->ev_used = 0;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_copy_meta_to_host(csr5b200_handle_t h, uint32_t *partition_pointer, uint32_t *partition_descriptor,
+                               int32_t *partition_descriptor_offset_pointer, int32_t *partition_descriptor_offset,
+                               void *calibrator)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
+    const Plan &pl = h->pl;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (pl.p == 0) return CSR5B200_SUCCESS;
+    const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+    if (partition_pointer) CU(h, cudaMemcpy(partition_pointer, pl.tile_ptr, (size_t)(pl.p + 1) * 4, k));
+    if (partition_descriptor)
+        CU(h, cudaMemcpy(partition_descriptor, pl.desc, (size_t)pl.p * OMEGA * pl.num_packet * 4, k));
+    if (partition_descriptor_offset_pointer)
+        CU(h, cudaMemcpy(partition_descriptor_offset_pointer, pl.desc_off_ptr, (size_t)(pl.p + 1) * 4, k));
+    if (partition_descriptor_offset && pl.num_offsets > 0)
+        CU(h, cudaMemcpy(partition_descriptor_offset, pl.desc_off, (size_t)pl.num_offsets * 4, k));
+    if (calibrator) CU(h, cudaMemcpy(calibrator, pl.calibrator, (size_t)pl.p * pl.value_bytes, k));
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_spmv_host(csr5b200_handle_t h, double alpha, const void *x_host, void *y_host)
+{
+    if (!h || !x_host || !y_host) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNSUPPORTED_CSR_SPMV;
+    const size_t vb = (size_t)h->pl.value_bytes;
+    if (!h->x_stage) CU(h, cudaMalloc(&h->x_stage, (size_t)(h->pl.n > 0 ? h->pl.n : 1) * vb));
+    if (!h->y_stage) CU(h, cudaMalloc(&h->y_stage, (size_t)(h->pl.m > 0 ? h->pl.m : 1) * vb));
+    CU(h, cudaMemcpyAsync(h->x_stage, x_host, (size_t)h->pl.n * vb, cudaMemcpyHostToDevice, h->stream));
+    const void *saved_x = h->pl.x;
+    h->pl.x = h->x_stage;
+    const int err = csr5b200_spmv(h, alpha, h->y_stage);
+    h->pl.x = saved_x;
+    if (err) return err;
+    CU(h, cudaMemcpyAsync(y_host, h->y_stage, (size_t)h->pl.m * vb, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_call_anonymouslib(int m, int n, int nnz, const int *row_ptr_host, const int *col_host,
+                               const void *val_host, const void *x_host, void *y_host, double alpha,
+                               int value_bytes, int sigma)
+{
+    csr5b200_handle_t h = nullptr;
+    int err = csr5b200_create(m, n, value_bytes, &h);
+    if (err) return err;
+    const size_t vb = (size_t)value_bytes;
+    int *d_rp = nullptr, *d_col = nullptr;
+    void *d_val = nullptr;
+    auto cleanup = [&](int code) {
+        csr5b200_free(h);
+        cudaFree(d_rp);
+        cudaFree(d_col);
+        cudaFree(d_val);
+        return code;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_rp, (size_t)(m + 1) * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&d_col, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int))) != cudaSuccess ||
+        (e = cudaMalloc(&d_val, (size_t)(nnz > 0 ? nnz : 1) * vb)) != cudaSuccess ||
+        (e = cudaMemcpy(d_rp, row_ptr_host, (size_t)(m + 1) * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_col, col_host, (size_t)nnz * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_val, val_host, (size_t)nnz * vb, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        h->last_cuda_error = (int)e;
+        return cleanup(CSR5B200_CUDA_ERROR);
+    }
+    if ((err = csr5b200_input_csr(h, nnz, d_rp, d_col, d_val))) return cleanup(err);
+    if ((err = csr5b200_set_sigma(h, sigma))) return cleanup(err);
+    if ((err = csr5b200_warmup(h))) return cleanup(err);
+    if ((err = csr5b200_as_csr5(h))) return cleanup(err);
+    if ((err = csr5b200_spmv_host(h, alpha, x_host, y_host))) return cleanup(err);
+    return cleanup(CSR5B200_SUCCESS);
+}
+
+const char *csr5b200_version(void) { return "csr5-b200 0.1 (sm_100a)"; }
+
+const char *csr5b200_error_string(int code)
+{
+    switch (code) {
+        case CSR5B200_SUCCESS: return "success";
+        case CSR5B200_UNKNOWN_FORMAT: return "unknown format (inputCSR not called)";
+        case CSR5B200_UNSUPPORTED_CSR5_OMEGA: return "unsupported CSR5 omega/sigma bit budget";
+        case CSR5B200_CSR_TO_CSR5_FAILED: return "CSR -> CSR5 conversion failed (sigma outside [4, 32]?)";
+        case CSR5B200_UNSUPPORTED_CSR_SPMV: return "spmv on CSR format: call asCSR5 first";
+        case CSR5B200_UNSUPPORTED_VALUE_TYPE: return "unsupported value type (use 4 or 8 bytes)";
+        case CSR5B200_CUDA_ERROR: return "CUDA runtime error (see csr5b200_info.last_cuda_error)";
+        case CSR5B200_INVALID_ARGUMENT: return "invalid argument";
+        default: return "unrecognised error code";
+    }
+}
+
+}  // extern "C"

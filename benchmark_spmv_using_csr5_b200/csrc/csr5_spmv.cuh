@@ -1,0 +1,508 @@
+// csr5_spmv.cuh -- the CSR5 SpMV kernels for sm_100a (included once per value type).
+//
+// One warp owns one omega x sigma tile (omega = 32), as in the reference
+// (csr5_spmv_cuda.h:275-311), but the data path and the write-back are re-designed:
+//
+//  * TMA-staged kernel (default): persistent CTAs; every warp runs its own S-deep ring of
+//    shared-memory slots that it fills with 1-D bulk TMA copies (cp.async.bulk -> UBLKCP) of the
+//    tile's val slab, col slab and descriptor words, completing on one mbarrier per slot.  The warp
+//    that consumes a slot is the warp that refills it, so there is no producer/consumer coupling
+//    between warps and no empty-barrier: S - 1 tiles (6 KB each at sigma 16 / FP64) are always in
+//    flight per warp while one is being reduced out of conflict-free shared memory.  x is gathered
+//    with LDG (read-only path); there is no reuse to stage.
+//  * direct-load kernel: one warp per tile, register-staged streaming loads (ld.global.cs), for
+//    arrays that are not 16-byte aligned and as the A/B comparison for the ncu captures.
+//
+//  * In-lane reduction: the sigma bit flags of a lane are unpacked ONCE into a 32-bit mask, so the
+//    fully unrolled loop tests compile-time bits instead of shifting a descriptor per element
+//    (csr5_spmv_cuda.h:146-176).
+//  * Cross-lane segmented sum: a backward segmented reduction by doubling with shuffles
+//    (5 steps) over the lanes that have no row start.  It is the same sum the reference forms as
+//    scan[l + seg_offset] - scan[l] + v[l] (csr5_spmv_cuda.h:25-38) without the subtraction, so it
+//    has no cancellation error and a fixed association order.
+//  * Write-back: every non-empty row is plain-stored exactly once by the tile in which it STARTS
+//    (including a row that starts exactly on a tile boundary, which the reference routes through
+//    the calibrator); only the carry-in of a tile whose first row started in an earlier tile goes
+//    to calibrator[t].  A second, tiny kernel adds the non-zero calibrators with FP64/FP32
+//    red.global.add.  Hence spmv() overwrites y and needs no zeroed y unless the matrix has empty
+//    rows before the tail (then y is memset first).  The reference's third launch, the tail
+//    kernel (csr5_spmv_cuda.h:384-419), is folded into the first: the leading warps of the grid
+//    reduce the rows of the last, partial tile CSR-vector style.
+#ifndef CSR5_SPMV_CUH
+#define CSR5_SPMV_CUH
+
+#include "csr5_internal.h"
+
+namespace csr5 {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+template <typename VT>
+struct SpmvArgs {
+    const int *__restrict__ row_ptr;
+    const int *__restrict__ col;
+    const VT *__restrict__ val;
+    const VT *__restrict__ x;
+    VT *__restrict__ y;
+    const uint32_t *__restrict__ tile_ptr;
+    const uint32_t *__restrict__ desc;
+    const int *__restrict__ desc_off_ptr;
+    const int *__restrict__ desc_off;
+    VT *__restrict__ cal;
+    VT alpha;
+    int m, p, bit_y, bit_all, num_packet;
+    int tail_start;      // first row of the tail tile
+    int tail_nnz_start;  // (p - 1) * omega * sigma
+    int tail_warps;      // ceil((m - tail_start) / 32)
+};
+
+// ---- small device helpers ---------------------------------------------------------------------
+
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+template <typename VT> __device__ __forceinline__ VT warp_sum_xor(VT v)
+{
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) v += __shfl_xor_sync(FULL_MASK, v, w);
+    return v;
+}
+
+// Lane flags from the packed descriptor words: bit i = element (lane, i) starts a row.
+__device__ __forceinline__ uint32_t unpack_flags(uint32_t w0, uint32_t w1, int bit_all, int sigma)
+{
+    const unsigned long long word = ((unsigned long long)w0 << 32) | w1;
+    uint32_t f = __brev((uint32_t)(word >> (32 - bit_all)));
+    if (sigma < 32) f &= (1u << sigma) - 1u;
+    return f;
+}
+
+// Where a tile's val / col / descriptor words come from.
+template <typename VT>
+struct GlobalTile {  // direct-load kernel: streaming loads, evict-first
+    static constexpr bool kStageInRegisters = true;  // issue all val/col loads of a chunk up front
+    const VT *val;
+    const int *col;
+    const uint32_t *desc;
+    __device__ __forceinline__ VT v(int i, int lane) const { return __ldcs(val + i * OMEGA + lane); }
+    __device__ __forceinline__ int c(int i, int lane) const { return __ldcs(col + i * OMEGA + lane); }
+    __device__ __forceinline__ uint32_t d(int k, int lane) const { return __ldg(desc + k * OMEGA + lane); }
+};
+
+template <typename VT>
+struct SharedTile {  // TMA-staged kernel: conflict-free LDS (consecutive lanes, consecutive words)
+    static constexpr bool kStageInRegisters = false;  // val/col are one LDS away: only x needs registers
+    const VT *val;
+    const int *col;
+    const uint32_t *desc;
+    __device__ __forceinline__ VT v(int i, int lane) const { return val[i * OMEGA + lane]; }
+    __device__ __forceinline__ int c(int i, int lane) const { return col[i * OMEGA + lane]; }
+    __device__ __forceinline__ uint32_t d(int k, int lane) const { return desc[k * OMEGA + lane]; }
+};
+
+// ---- one CSR5 tile (t < p - 1) ------------------------------------------------------------------
+template <typename VT, int SIGMA, typename Tile>
+__device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &tile, int t, int lane,
+                                             uint32_t raw_start, uint32_t raw_stop)
+{
+    // Elements are consumed in register chunks so that all streaming loads and x gathers of a chunk
+    // are in flight together without spilling at sigma = 32.
+    constexpr int CH = SIGMA <= 16 ? SIGMA : (SIGMA + 1) / 2;
+    const int row_start = (int)(raw_start & ROW_MASK);
+    const int row_stop = (int)(raw_stop & ROW_MASK);
+    const VT *__restrict__ x = a.x;
+
+    if (raw_start == (uint32_t)row_stop) {
+        // fast track: the whole tile lies inside one row (csr5_spmv_cuda.h:59-89)
+        VT sum = 0;
+#pragma unroll
+        for (int c0 = 0; c0 < SIGMA; c0 += CH) {
+            VT v[CH], xv[CH];
+            int c[CH];
+            if constexpr (Tile::kStageInRegisters) {
+#pragma unroll
+                for (int k = 0; k < CH; k++)
+                    if (c0 + k < SIGMA) { c[k] = tile.c(c0 + k, lane); v[k] = tile.v(c0 + k, lane); }
+            }
+#pragma unroll
+            for (int k = 0; k < CH; k++)
+                if (c0 + k < SIGMA) xv[k] = __ldg(x + (Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane)));
+#pragma unroll
+            for (int k = 0; k < CH; k++)
+                if (c0 + k < SIGMA)
+                    sum = fma_t<VT>(Tile::kStageInRegisters ? v[k] : tile.v(c0 + k, lane), xv[k], sum);
+        }
+        sum = warp_sum_xor<VT>(sum);
+        if (lane == 0) {
+            const bool starts_here = (tile.d(0, 0) >> (31 - a.bit_all)) & 1u;  // raw flag of element 0
+            if (starts_here) { a.y[row_start] = a.alpha * sum; a.cal[t] = (VT)0; }
+            else a.cal[t] = a.alpha * sum;
+        }
+        return;
+    }
+
+    const bool dirty = raw_start >> 31;
+    const uint32_t w0 = tile.d(0, lane);
+    const uint32_t w1 = a.num_packet > 1 ? tile.d(1, lane) : 0u;
+    const uint32_t f = unpack_flags(w0, w1, a.bit_all, SIGMA);
+    const uint32_t ff = f | (lane == 0 ? 1u : 0u);  // lane 0 always opens a segment (…:138)
+    int y_idx = (int)(w0 >> (32 - a.bit_y));
+    const int *__restrict__ yoff = dirty ? a.desc_off + a.desc_off_ptr[t] : nullptr;
+    VT *__restrict__ Y = a.y + row_start + 1;
+
+    // `open`: the running segment began in this lane at a real row start, so it is stored
+    // directly when it closes.  Lane 0's first segment (row_start itself) is handled at the end.
+    bool open = (ff & 1u) && lane != 0;
+    VT sum = 0, first_sum = 0;
+#pragma unroll
+    for (int c0 = 0; c0 < SIGMA; c0 += CH) {
+        VT v[CH], xv[CH];
+        int c[CH];
+        if constexpr (Tile::kStageInRegisters) {
+#pragma unroll
+            for (int k = 0; k < CH; k++)
+                if (c0 + k < SIGMA) { c[k] = tile.c(c0 + k, lane); v[k] = tile.v(c0 + k, lane); }
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k++)
+            if (c0 + k < SIGMA) xv[k] = __ldg(x + (Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane)));
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const int i = c0 + k;
+            if (i < SIGMA) {
+                if (i > 0 && ((ff >> i) & 1u)) {
+                    if (open) { Y[dirty ? yoff[y_idx] : y_idx] = a.alpha * sum; y_idx++; }
+                    else first_sum = sum;
+                    open = true;
+                    sum = 0;
+                }
+                sum = fma_t<VT>(Tile::kStageInRegisters ? v[k] : tile.v(i, lane), xv[k], sum);
+            }
+        }
+    }
+    if (!open) first_sum = sum;  // no row start after element 0: the whole lane is one piece
+    VT last_sum = sum;
+
+    // Cross-lane step.  carry[l] = piece of lane l that belongs to a segment opened in an earlier
+    // lane (lanes whose element 0 is not a row start).  Lane l with a row start collects the
+    // carries of lanes l+1 .. l+seg_offset+1, i.e. up to and including the next lane with a start.
+    const VT carry = (ff & 1u) ? (VT)0 : first_sum;
+    VT acc = __shfl_down_sync(FULL_MASK, carry, 1);
+    if (lane == 31) acc = 0;
+    const uint32_t present = __ballot_sync(FULL_MASK, ff != 0);
+    const uint32_t following = lane == 31 ? 0u : present >> (lane + 1);
+    const int rem = following ? __ffs(following) - 1 : 31 - lane;  // == seg_offset on lanes with a start
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const VT nb = __shfl_down_sync(FULL_MASK, acc, d);
+        if (d <= rem) acc += nb;
+    }
+    if (ff) last_sum += acc;
+
+    if (open) Y[dirty ? yoff[y_idx] : y_idx] = a.alpha * last_sum;
+    if (lane == 0) {
+        const VT head = open ? first_sum : last_sum;  // lane 0's first segment = row_start's piece
+        if (f & 1u) { a.y[row_start] = a.alpha * head; a.cal[t] = (VT)0; }  // row starts on the tile boundary
+        else a.cal[t] = a.alpha * head;                                      // carry-in from earlier tiles
+    }
+}
+
+// ---- rows of the tail tile: 32 rows per warp, CSR-vector per non-empty row ----------------------
+template <typename VT>
+__device__ __forceinline__ void process_tail_rows(const SpmvArgs<VT> &a, int tw, int lane)
+{
+    const int r = a.tail_start + tw * 32 + lane;
+    int ra = 0, rb = 0;
+    bool carried = false;
+    if (r < a.m) {
+        ra = __ldg(a.row_ptr + r);
+        rb = __ldg(a.row_ptr + r + 1);
+        if (r == a.tail_start) { carried = ra != a.tail_nnz_start; ra = a.tail_nnz_start; }
+    }
+    VT mine = 0;
+    uint32_t todo = __ballot_sync(FULL_MASK, rb > ra);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int ja = __shfl_sync(FULL_MASK, ra, j), jb = __shfl_sync(FULL_MASK, rb, j);
+        VT s = 0;
+        for (int k = ja + lane; k < jb; k += 32) s = fma_t<VT>(__ldcs(a.val + k), __ldg(a.x + __ldcs(a.col + k)), s);
+        s = warp_sum_xor<VT>(s);
+        if (lane == j) mine = s;
+    }
+    if (r < a.m) {
+        if (carried) a.cal[a.p - 1] = a.alpha * mine;
+        else {
+            a.y[r] = a.alpha * mine;
+            if (r == a.tail_start) a.cal[a.p - 1] = (VT)0;
+        }
+    }
+}
+
+// ---- direct-load kernel ---------------------------------------------------------------------------
+template <typename VT, int SIGMA, int WPB>
+__global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT> a)
+{
+    const int lane = threadIdx.x & 31;
+    const long long unit = (long long)blockIdx.x * WPB + (threadIdx.x >> 5);
+    if (unit < a.tail_warps) { process_tail_rows<VT>(a, (int)unit, lane); return; }
+    const long long tl = unit - a.tail_warps;
+    if (tl >= a.p - 1) return;
+    const int t = (int)tl;
+    const size_t base = (size_t)t * (OMEGA * SIGMA);
+    GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet};
+    process_tile<VT, SIGMA>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
+}
+
+// ---- TMA-staged persistent kernel ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk TMA copy global -> shared, completing (complete_tx) on an mbarrier; streamed through L2
+// with an evict-first policy since every matrix byte is read once per SpMV.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                            uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+constexpr int TMA_MAX_WARPS = 16;
+
+template <typename VT, int SIGMA>
+struct TmaSlot {
+    static constexpr int VAL_BYTES = OMEGA * SIGMA * (int)sizeof(VT);
+    static constexpr int COL_BYTES = OMEGA * SIGMA * 4;
+    static constexpr int DESC_BYTES_MAX = OMEGA * 2 * 4;
+    static constexpr int BYTES = VAL_BYTES + COL_BYTES + DESC_BYTES_MAX;  // multiple of 128
+};
+
+// grid = persistent CTAs; warp gw handles tiles gw, gw + GW, gw + 2 GW, ... (GW = warps in the grid)
+template <typename VT, int SIGMA>
+__global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const SpmvArgs<VT> a, const int stages)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    using Slot = TmaSlot<VT, SIGMA>;
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const long long GW = (long long)gridDim.x * wpb;
+    const long long gw = (long long)blockIdx.x * wpb + w;
+
+    // smem: [wpb][stages] slots, then [wpb][stages] mbarriers
+    unsigned char *my_slots = smem + (size_t)w * stages * Slot::BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)wpb * stages * Slot::BYTES) + w * stages;
+    if (lane == 0) {
+        for (int s = 0; s < stages; s++) mbar_init(smem_u32(bars + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    // tail rows first (they are few); warps stride over them
+    for (long long tw = gw; tw < a.tail_warps; tw += GW) process_tail_rows<VT>(a, (int)tw, lane);
+
+    const long long ntiles = a.p - 1;
+    const uint32_t desc_bytes = OMEGA * 4 * a.num_packet;
+    const uint32_t tx_bytes = Slot::VAL_BYTES + Slot::COL_BYTES + desc_bytes;
+    const uint64_t policy = l2_evict_first_policy();
+
+    auto issue = [&](long long t, int s) {  // lane 0 only
+        unsigned char *slot = my_slots + (size_t)s * Slot::BYTES;
+        const uint32_t bar = smem_u32(bars + s);
+        const size_t base = (size_t)t * (OMEGA * SIGMA);
+        mbar_expect_tx(bar, tx_bytes);
+        tma_load_1d(smem_u32(slot), a.val + base, Slot::VAL_BYTES, bar, policy);
+        tma_load_1d(smem_u32(slot + Slot::VAL_BYTES), a.col + base, Slot::COL_BYTES, bar, policy);
+        tma_load_1d(smem_u32(slot + Slot::VAL_BYTES + Slot::COL_BYTES),
+                    a.desc + (size_t)t * OMEGA * a.num_packet, desc_bytes, bar, policy);
+    };
+
+    // prologue: fill the ring
+    if (lane == 0) {
+        long long t = gw;
+        for (int s = 0; s < stages && t < ntiles; s++, t += GW) issue(t, s);
+    }
+    uint32_t raw_start = 0, raw_stop = 0;
+    if (gw < ntiles) { raw_start = __ldg(a.tile_ptr + gw); raw_stop = __ldg(a.tile_ptr + gw + 1); }
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (long long t = gw; t < ntiles; t += GW) {
+        // tile_ptr words of the next tile are fetched one iteration ahead
+        const long long tn = t + GW;
+        uint32_t nstart = 0, nstop = 0;
+        if (tn < ntiles) { nstart = __ldg(a.tile_ptr + tn); nstop = __ldg(a.tile_ptr + tn + 1); }
+
+        mbar_wait(smem_u32(bars + s), parity);
+        const unsigned char *slot = my_slots + (size_t)s * Slot::BYTES;
+        SharedTile<VT> tile{reinterpret_cast<const VT *>(slot),
+                            reinterpret_cast<const int *>(slot + Slot::VAL_BYTES),
+                            reinterpret_cast<const uint32_t *>(slot + Slot::VAL_BYTES + Slot::COL_BYTES)};
+        process_tile<VT, SIGMA>(a, tile, (int)t, lane, raw_start, raw_stop);
+
+        // this warp is done reading slot s: refill it with the tile `stages` iterations ahead
+        __syncwarp();
+        const long long tf = t + (long long)stages * GW;
+        if (lane == 0 && tf < ntiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(tf, s);
+        }
+        raw_start = nstart;
+        raw_stop = nstop;
+        if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+}
+
+// ---- carries: y[row of tile t] += calibrator[t] for the tiles whose first row began earlier -----
+template <typename VT>
+__global__ void __launch_bounds__(256)
+calibrate_kernel(const uint32_t *__restrict__ tile_ptr, const VT *__restrict__ cal, VT *__restrict__ y, int p)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p) return;
+    const VT c = cal[t];
+    if (c != (VT)0) atomicAdd(y + (tile_ptr[t] & ROW_MASK), c);
+}
+
+// ---- host-side dispatch ----------------------------------------------------------------------------
+template <typename VT, int SIGMA>
+cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_ok, cudaStream_t stream,
+                         int *used)
+{
+    const long long ntiles = a.p - 1;
+    int kernel = tn.kernel;
+    if (kernel == 0) kernel = tma_ok ? 2 : 1;
+    if (kernel == 2 && !tma_ok) kernel = 1;
+    if (ntiles <= 0) kernel = 1;
+    *used = kernel;
+
+    if (kernel == 1) {
+        constexpr int WPB = 4;
+        const long long units = ntiles + a.tail_warps;
+        const long long blocks = (units + WPB - 1) / WPB;
+        if (blocks <= 0) return cudaSuccess;
+        spmv_direct_kernel<VT, SIGMA, WPB><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
+
+    // Ring geometry: as many self-prefetching warps per SM as fit with `stages` slots each.
+    using Slot = TmaSlot<VT, SIGMA>;
+    const size_t per_slot = Slot::BYTES + 8;            // slot + its mbarrier
+    const size_t smem_sm = 216 * 1024;                  // of 227 KB; leaves the per-CTA reserve
+    int stages = tn.tma_stages > 0 ? tn.tma_stages : 3;
+    if (stages > 8) stages = 8;
+    int wps = (int)(smem_sm / (stages * per_slot));     // warps per SM
+    while (wps < 4 && stages > 2) { stages--; wps = (int)(smem_sm / (stages * per_slot)); }
+    if (wps < 1) wps = 1;
+    if (wps > 32) wps = 32;
+    int ctas_per_sm = tn.ctas_per_sm > 0 ? tn.ctas_per_sm : (wps + 7) / 8;
+    int warps = tn.tma_warps > 0 ? tn.tma_warps : wps / ctas_per_sm;
+    if (warps > TMA_MAX_WARPS) warps = TMA_MAX_WARPS;
+    if (warps < 1) warps = 1;
+    while (warps > 1 && (size_t)warps * stages * per_slot > (size_t)226 * 1024) warps--;
+    const size_t smem = (size_t)warps * stages * (Slot::BYTES + 8);
+    static bool attr_set = false;  // per (VT, SIGMA) instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(spmv_tma_kernel<VT, SIGMA>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    long long grid = (long long)tn.num_sms * ctas_per_sm;
+    const long long need = (ntiles + warps - 1) / warps;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    spmv_tma_kernel<VT, SIGMA><<<(unsigned)grid, warps * 32, smem, stream>>>(a, stages);
+    return cudaGetLastError();
+}
+
+template <typename VT>
+cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y, cudaStream_t stream,
+                          int *used, int *launches)
+{
+    *used = 0;
+    *launches = 0;
+    if (pl.m <= 0) return cudaSuccess;
+    cudaError_t e;
+    if (pl.needs_zero_fill || pl.p == 0) {
+        e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
+        if (e != cudaSuccess) return e;
+        ++*launches;
+        if (pl.p == 0) return cudaSuccess;
+    }
+    SpmvArgs<VT> a;
+    a.row_ptr = pl.row_ptr;
+    a.col = pl.col;
+    a.val = static_cast<const VT *>(pl.val);
+    a.x = static_cast<const VT *>(pl.x);
+    a.y = y;
+    a.tile_ptr = pl.tile_ptr;
+    a.desc = pl.desc;
+    a.desc_off_ptr = pl.desc_off_ptr;
+    a.desc_off = pl.desc_off;
+    a.cal = static_cast<VT *>(pl.calibrator);
+    a.alpha = alpha;
+    a.m = pl.m;
+    a.p = pl.p;
+    a.bit_y = pl.bit_y;
+    a.bit_all = pl.bit_y + pl.bit_ss;
+    a.num_packet = pl.num_packet;
+    a.tail_start = pl.tail_start;
+    a.tail_nnz_start = (pl.p - 1) * OMEGA * pl.sigma;
+    a.tail_warps = (pl.m - pl.tail_start + 31) / 32;
+
+    // bulk TMA needs 16-byte aligned global addresses; tile strides are multiples of 128 bytes
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(a.val) % 16 == 0) &&
+                        (reinterpret_cast<uintptr_t>(a.col) % 16 == 0) &&
+                        (reinterpret_cast<uintptr_t>(a.desc) % 16 == 0);
+
+    if (tn.ev_begin && (e = cudaEventRecord(tn.ev_begin, stream)) != cudaSuccess) return e;
+    switch (pl.sigma) {
+#define CSR5_CASE(S) case S: e = launch_sigma<VT, S>(a, tn, tma_ok, stream, used); break;
+        CSR5_CASE(4) CSR5_CASE(5) CSR5_CASE(6) CSR5_CASE(7) CSR5_CASE(8) CSR5_CASE(9) CSR5_CASE(10)
+        CSR5_CASE(11) CSR5_CASE(12) CSR5_CASE(13) CSR5_CASE(14) CSR5_CASE(15) CSR5_CASE(16)
+        CSR5_CASE(17) CSR5_CASE(18) CSR5_CASE(19) CSR5_CASE(20) CSR5_CASE(21) CSR5_CASE(22)
+        CSR5_CASE(23) CSR5_CASE(24) CSR5_CASE(25) CSR5_CASE(26) CSR5_CASE(27) CSR5_CASE(28)
+        CSR5_CASE(29) CSR5_CASE(30) CSR5_CASE(31) CSR5_CASE(32)
+#undef CSR5_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    if (tn.ev_end && (e = cudaEventRecord(tn.ev_end, stream)) != cudaSuccess) return e;
+    ++*launches;
+    const int threads = 256;
+    calibrate_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a.tile_ptr, a.cal, y, pl.p);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace csr5
+
+#endif

@@ -1,0 +1,287 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes ->
+libcsr5_b200.so), against the oracle on the same seeded inputs.
+
+Bars: CSR5 metadata word-for-word; y bit-exact on the reference's integer-valued input
+distribution (main.cu:314-326); FP64 real-valued y within 1e-12 rel (north_star: 1e-6);
+FP32 real-valued within 2e-5 rel of an FP64-accumulated scalar loop."""
+import numpy as np
+import pytest
+
+from benchmark_spmv_using_csr5_b200 import matrices as M
+from tests.cases import sigma_sweep_case, small_cases
+
+pytestmark = pytest.mark.gpu
+CASES = small_cases()
+FP64_RTOL = 1e-12
+FP32_RTOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _upload(torch, A, val, x):
+    dev = "cuda"
+    return (torch.from_numpy(A.row_ptr).to(dev), torch.from_numpy(A.col).to(dev),
+            torch.from_numpy(val).to(dev), torch.from_numpy(x).to(dev))
+
+
+def _handle(torch, A, val, x, sigma, kernel=0):
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    tdt = torch.float64 if val.dtype == np.float64 else torch.float32
+    rp, ci, v, xd = _upload(torch, A, val, x)
+    h = H.anonymouslibHandle(A.m, A.n, tdt)
+    assert h.inputCSR(A.nnz, rp, ci, v) == 0
+    assert h.setX(xd) == 0
+    h.setSigma(sigma)
+    assert h.set_option(H.OPT_KERNEL, kernel) == 0
+    assert h.warmup() == 0
+    assert h.asCSR5() == 0
+    return h, (rp, ci, v, xd)
+
+
+def _spmv(torch, h, m, dtype, alpha=1.0, fill=float("nan")):
+    y = torch.full((m,), fill, device="cuda", dtype=dtype)  # garbage-filled: spmv must overwrite
+    assert h.spmv(alpha, y) == 0
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "tma"])
+@pytest.mark.parametrize("name,A,sigma", CASES, ids=[c[0] for c in CASES])
+def test_y_int_bit_exact_and_real(torch_cuda, oracle, name, A, sigma, kernel):
+    torch = torch_cuda
+    for kind in ("int", "real"):
+        val, x = M.values(A.nnz, A.n, kind)
+        h, _keep = _handle(torch, A, val, x, sigma, kernel)
+        y = _spmv(torch, h, A.m, torch.float64)
+        y_oracle = oracle.csr5_spmv(A.m, A.n, A.row_ptr, A.col, val, x, sigma)
+        y_scalar = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+        if kind == "int":
+            assert np.array_equal(y, y_oracle), f"{name}: differs from CSR5_cuda oracle"
+            assert np.array_equal(y, y_scalar), f"{name}: differs from scalar CSR"
+        else:
+            assert np.allclose(y, y_oracle, rtol=FP64_RTOL, atol=0), name
+            assert np.allclose(y, y_scalar, rtol=FP64_RTOL, atol=0), name
+        assert h.destroy() == 0
+        h.free()
+
+
+@pytest.mark.parametrize("name,A,sigma", CASES, ids=[c[0] for c in CASES])
+def test_metadata_word_for_word(torch_cuda, oracle, name, A, sigma):
+    torch = torch_cuda
+    if A.nnz == 0:
+        pytest.skip("empty")
+    val, x = M.values(A.nnz, A.n, "int")
+    h, _keep = _handle(torch, A, val, x, sigma)
+    got = h.meta_to_host()
+    s = sigma if sigma > 0 else oracle.auto_sigma(A.m, A.nnz)
+    want = oracle.csr5_meta(A.m, A.nnz, s, A.row_ptr)
+    assert (got["sigma"], got["bit_y"], got["bit_ss"], got["num_packet"], got["p"]) == \
+        (want.sigma, want.bit_y, want.bit_ss, want.num_packet, want.p)
+    assert got["tail_start"] == want.tail_start
+    assert np.array_equal(got["tile_ptr"], want.tile_ptr), "tile_ptr"
+    assert np.array_equal(got["desc"], want.desc), "tile_desc"
+    assert got["num_offsets"] == want.num_offsets
+    assert np.array_equal(got["desc_off_ptr"], want.desc_off_ptr), "desc_offset_ptr"
+    assert np.array_equal(got["desc_off"], want.desc_off), "desc_offset"
+    # transposed arrays as the reference's handle would hold them
+    _rp, ci, v, _x = _keep
+    torch.cuda.synchronize()
+    assert np.array_equal(ci.cpu().numpy(), oracle.transpose(A.col, s, A.nnz, want.tile_ptr, True)), "col5"
+    assert np.array_equal(v.cpu().numpy(), oracle.transpose(val, s, A.nnz, want.tile_ptr, True)), "val5"
+    # asCSR restores the caller's arrays bit for bit
+    assert h.asCSR() == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(ci.cpu().numpy(), A.col)
+    assert np.array_equal(v.cpu().numpy(), val)
+    h.free()
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "tma"])
+def test_all_sigmas(torch_cuda, oracle, kernel):
+    torch = torch_cuda
+    A = sigma_sweep_case()
+    val, x = M.values(A.nnz, A.n, "int")
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    for sigma in range(4, 33):
+        h, _keep = _handle(torch, A, val, x, sigma, kernel)
+        y = _spmv(torch, h, A.m, torch.float64)
+        assert np.array_equal(y, y_ref), sigma
+        h.free()
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "tma"])
+def test_fp32(torch_cuda, oracle, kernel):
+    torch = torch_cuda
+    for name, A, sigma in CASES:
+        val, x = M.values(A.nnz, A.n, "int", np.float32)
+        h, _keep = _handle(torch, A, val, x, sigma, kernel)
+        y = _spmv(torch, h, A.m, torch.float32)
+        assert np.array_equal(y, oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)), name
+        h.free()
+        val, x = M.values(A.nnz, A.n, "real", np.float32)
+        h, _keep = _handle(torch, A, val, x, sigma, kernel)
+        y = _spmv(torch, h, A.m, torch.float32)
+        y64 = oracle.csr_spmv_f32_acc64(A.m, A.row_ptr, A.col, val, x)
+        assert np.allclose(y, y64, rtol=FP32_RTOL, atol=1e-5), name
+        h.free()
+
+
+def test_repeated_spmv_is_idempotent_and_alpha_honoured(torch_cuda, oracle):
+    """The reference drifts on repeated calls and ignores alpha (s0-1); the
+    replacement overwrites y and honours alpha, with a bug-compat switch for alpha."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    name, A, sigma = CASES[4]
+    val, x = M.values(A.nnz, A.n, "int")
+    h, _keep = _handle(torch, A, val, x, sigma)
+    y = torch.zeros(A.m, device="cuda", dtype=torch.float64)
+    for _ in range(5):
+        assert h.spmv(1.0, y) == 0
+    torch.cuda.synchronize()
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    assert np.array_equal(y.cpu().numpy(), y_ref)
+    assert np.array_equal(_spmv(torch, h, A.m, torch.float64, alpha=3.0), 3.0 * y_ref)
+    h.set_option(H.OPT_IGNORE_ALPHA, 1)
+    assert np.array_equal(_spmv(torch, h, A.m, torch.float64, alpha=3.0), y_ref)
+    h.free()
+
+
+def test_error_codes(torch_cuda):
+    """detail/common.h:13-18 and the call-order rules of anonymouslib_cuda.h."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    A = M.banded(512, 16)
+    val, x = M.values(A.nnz, A.n, "int")
+    rp, ci, v, xd = _upload(torch, A, val, x)
+    y = torch.zeros(A.m, device="cuda", dtype=torch.float64)
+    h = H.anonymouslibHandle(A.m, A.n)
+    assert h.asCSR5() == H.ANONYMOUSLIB_UNKOWN_FORMAT          # before inputCSR
+    assert h.inputCSR(A.nnz, rp, ci, v) == 0
+    h.setX(xd)
+    assert h.spmv(1.0, y) == H.ANONYMOUSLIB_UNSUPPORTED_CSR_SPMV  # anonymouslib_cuda.h:266-269
+    h.setSigma(3)
+    assert h.asCSR5() == H.ANONYMOUSLIB_CSR_TO_CSR5_FAILED     # sigma outside [4, 32]
+    h.setSigma(40)
+    assert h.asCSR5() == H.ANONYMOUSLIB_CSR_TO_CSR5_FAILED
+    h.setSigma(H.ANONYMOUSLIB_AUTO_TUNED_SIGMA)
+    assert h.asCSR5() == 0 and h.asCSR5() == 0                 # second call is a no-op
+    assert h.info().sigma == 16
+    assert h.asCSR() == 0 and h.asCSR() == 0
+    assert h.destroy() == 0
+    h.free()
+    with pytest.raises(TypeError):
+        H.anonymouslibHandle(4, 4, torch.float16)
+
+
+def test_host_entry_points(torch_cuda, oracle):
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    name, A, sigma = CASES[5]
+    for dt in (np.float64, np.float32):
+        val, x = M.values(A.nnz, A.n, "int", dt)
+        y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+        y = H.call_anonymouslib(A.m, A.n, A.nnz, A.row_ptr, A.col, val, x, 1.0, sigma)
+        assert np.array_equal(y, y_ref)
+        h, _keep = _handle(torch, A, val, x, sigma)
+        xp = torch.from_numpy(x).pin_memory()
+        yp = torch.empty(A.m, dtype=xp.dtype).pin_memory()
+        assert h.spmv_host(1.0, xp, yp) == 0
+        assert np.array_equal(yp.numpy(), y_ref)
+        y2 = np.empty(A.m, dt)
+        assert h.spmv_host(2.0, x, y2) == 0
+        assert np.array_equal(y2, 2 * y_ref)
+        h.free()
+
+
+def test_empty_matrix(torch_cuda):
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    m = 100
+    rp = torch.zeros(m + 1, device="cuda", dtype=torch.int32)
+    ci = torch.zeros(1, device="cuda", dtype=torch.int32)
+    v = torch.zeros(1, device="cuda", dtype=torch.float64)
+    x = torch.ones(m, device="cuda", dtype=torch.float64)
+    h = H.anonymouslibHandle(m, m)
+    assert h.inputCSR(0, rp, ci, v) == 0
+    h.setX(x)
+    h.setSigma(-1)
+    assert h.asCSR5() == 0
+    y = torch.full((m,), 7.0, device="cuda", dtype=torch.float64)
+    assert h.spmv(1.0, y) == 0
+    torch.cuda.synchronize()
+    assert float(y.abs().sum()) == 0.0
+    h.free()
+
+
+def test_non_default_stream(torch_cuda, oracle):
+    torch = torch_cuda
+    name, A, sigma = CASES[0]
+    val, x = M.values(A.nnz, A.n, "int")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        h, _keep = _handle(torch, A, val, x, sigma)
+        y = torch.empty(A.m, device="cuda", dtype=torch.float64)
+        assert h.spmv(1.0, y) == 0
+    s.synchronize()
+    assert np.array_equal(y.cpu().numpy(), oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x))
+    h.free()
+
+
+# ---- BASELINE.json full sizes: size-independent properties, evaluated on the device ------------
+
+def _segment_sums_exact(torch, rp, ci, v, x):
+    """Exact y for integer-valued inputs: prefix sums of the products are exact in FP64 below 2^53."""
+    prod = v.double() * x.double()[ci.long()]
+    cs = torch.zeros(prod.numel() + 1, device=prod.device, dtype=torch.float64)
+    torch.cumsum(prod, 0, out=cs[1:])
+    return cs[rp[1:].long()] - cs[rp[:-1].long()]
+
+
+def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2)):
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    m, n, nnz = rp.numel() - 1, x.numel(), ci.numel()
+    y_ref = _segment_sums_exact(torch, rp, ci, v, x).to(dtype)
+    col0, val0 = ci.clone(), v.clone()
+    for kernel in kernels:
+        h = H.anonymouslibHandle(m, n, dtype)
+        assert h.inputCSR(nnz, rp, ci, v) == 0
+        h.setX(x)
+        h.setSigma(-1)
+        h.set_option(H.OPT_KERNEL, kernel)
+        assert h.asCSR5() == 0
+        y = torch.full((m,), float("nan"), device="cuda", dtype=dtype)
+        assert h.spmv(1.0, y) == 0
+        assert torch.equal(y, y_ref), f"kernel {kernel}: y differs from exact segment sums"
+        # linearity: A(2x) == 2 A x exactly for integer data
+        x2 = (2 * x).contiguous()
+        h.setX(x2)
+        y2 = torch.empty_like(y)
+        assert h.spmv(1.0, y2) == 0
+        assert torch.equal(y2, 2 * y_ref)
+        h.setX(x)
+        assert h.destroy() == 0   # round trip restores the caller's arrays
+        assert torch.equal(ci, col0) and torch.equal(v, val0)
+        h.free()
+
+
+def test_full_size_c2_banded(torch_cuda):
+    """BASELINE.json configs[1]: banded 10M x 10M, 16 nnz/row, FP64."""
+    torch = torch_cuda
+    m = 10_000_000
+    rp, ci = M.device_banded(m, 16)
+    v, x = M.device_values(ci.numel(), m, "int", torch.float64, "cuda")
+    _full_size_check(torch, rp, ci, v, x, torch.float64)
+
+
+def test_full_size_c3_rmat22(torch_cuda):
+    """BASELINE.json configs[2]: R-MAT scale 22, ~64M nnz, FP64 (52 % empty rows, hub rows)."""
+    torch = torch_cuda
+    rp, ci = M.device_rmat(22)
+    n = rp.numel() - 1
+    v, x = M.device_values(ci.numel(), n, "int", torch.float64, "cuda")
+    _full_size_check(torch, rp, ci, v, x, torch.float64)

@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- CSR5 SpMV on B200: GFLOPS and achieved HBM GB/s against the streaming roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference]
+
+A step is one SpMV (y = A x) over the resident matrix, the unit the reference times in its
+benchmark loop (CSR5_cuda/main.cu:93-106: NUM_RUN back-to-back spmv() between two events).
+N = 1 workload = BASELINE.json configs[1]: banded 10M x 10M, 16 nnz/row, FP64.  N > 1: one process
+per GPU (torchrun), weak scaling -- rank g owns the row range [g*m, (g+1)*m) of the N*m-row banded
+matrix (its own CSR5 arrays), x is replicated, and every step ends with the all-gather of the y
+segments over NCCL/NVLink.
+
+One JSON line on stdout (rank 0).  `value` = whole-job GFLOPS with everything resident in HBM;
+`e2e` = the same through the host-buffer C-ABI call (csr5b200_spmv_host: pinned x H2D + SpMV +
+y D2H every step); `roofline` = algorithmic bytes / live CUDA-event duration of the main SpMV kernel
+against the measured HBM copy bandwidth; `cpu_baseline` = the reference's own CSR5_avx2 backend
+(oracle/_ref, compiled from /root/reference) on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": "banded 10M x 10M, 16 nnz/row, FP64 (BASELINE.json configs[1])",
+    "c3": "R-MAT scale 22, edge factor 16, FP64 (BASELINE.json configs[2])",
+    "c4": "27-pt Laplacian 320^3, FP32 (BASELINE.json configs[3])",
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sampled DURING the timed regions
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """NVML sampler thread (falls back to one-shot nvidia-smi queries)."""
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period = index, period_s
+        self.samples = []  # (t, sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] NVML unavailable ({e}); falling back to nvidia-smi")
+
+    def _one(self):
+        if self._nvml is not None:
+            n = self._nvml
+            mhz = float(n.nvmlDeviceGetClockInfo(self._dev, n.NVML_CLOCK_SM))
+            try:
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._dev))
+            except Exception:
+                rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev))
+            return mhz, rs
+        out = subprocess.run(
+            ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+             "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout.strip()
+        a = [t.strip() for t in out.split(",")]
+        self.max_mhz = float(a[1])
+        return float(a[0]), int(a[2], 16)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                mhz, rs = self._one()
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=5)
+
+    def summary(self, windows):
+        """windows: list of (t0, t1) host timestamps of the timed regions."""
+        inside = [(m, r) for (t, m, r) in self.samples if any(a <= t <= b for a, b in windows)]
+        used = inside if inside else [(m, r) for (_, m, r) in self.samples]
+        mask = 0
+        for _, r in used:
+            mask |= r
+        reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit and name != "gpu_idle")
+        return {"sm_mhz": float(np.median([m for m, _ in used])) if used else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(used),
+                "sampled": "in timed regions" if inside else "whole run"}
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def build_workload(name, torch, device, rank, world):
+    """-> dict(row_ptr, col, val, x, m (local rows), n, row_begin, dtype, desc)"""
+    from benchmark_spmv_using_csr5_b200 import matrices as M
+    if name == "c2":
+        m_local = 10_000_000
+        n = m_local * world
+        rp, ci = M.device_banded(n, 16, device, row_begin=rank * m_local, rows=m_local, n=n)
+        dtype = torch.float64
+        val, _ = M.device_values(ci.numel(), 1, "real", dtype, device, seed=42 + rank)
+        _, x = M.device_values(1, n, "real", dtype, device, seed=4242)  # same x on every rank
+        return dict(row_ptr=rp, col=ci, val=val, x=x, m=m_local, n=n, row_begin=rank * m_local, dtype=dtype)
+    if world != 1:
+        raise SystemExit(f"workload {name} is a single-GPU configuration")
+    if name == "c3":
+        rp, ci = M.device_rmat(22, device=device)
+        n = rp.numel() - 1
+        dtype = torch.float64
+    elif name == "c4":
+        rp, ci, val = M.device_laplacian27(320, device=device, dtype=torch.float32)
+        n = rp.numel() - 1
+        dtype = torch.float32
+        _, x = M.device_values(1, n, "real", dtype, device, seed=42)
+        return dict(row_ptr=rp, col=ci, val=val, x=x, m=n, n=n, row_begin=0, dtype=dtype)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    val, x = M.device_values(ci.numel(), n, "real", dtype, device, seed=42)
+    return dict(row_ptr=rp, col=ci, val=val, x=x, m=n, n=n, row_begin=0, dtype=dtype)
+
+
+def algorithmic_bytes(m, n, nnz, vb):
+    """compulsory CSR traffic, each array touched once."""
+    return nnz * (vb + 4) + (m + 1) * 4 + n * vb + m * vb
+
+
+def reference_getB(m, nnz, vb):
+    """detail/utils.h:10-14 (counts one x read per nnz) -- for comparability with the reference's print."""
+    return (m + 1 + nnz) * 4 + (2 * nnz + m) * vb
+
+
+def exact_check(torch, w, y):
+    """max_i |y_i - ref_i| / sum_j |a_ij x_j| with ref = per-row FP64 sums evaluated on the device by
+    an independent route (torch index_add_ of the FP64 products onto their row; col/val must be in CSR
+    order).  For the all-positive C2/C3 inputs this is the plain relative error; for the signed
+    Laplacian it is the usual row-wise backward-error normalisation."""
+    m = w["row_ptr"].numel() - 1
+    counts = (w["row_ptr"][1:] - w["row_ptr"][:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(m, device=counts.device), counts)
+    prod = w["val"].double() * w["x"].double()[w["col"].long()]
+    ref = torch.zeros(m, device=prod.device, dtype=torch.float64).index_add_(0, rows, prod)
+    scale = torch.zeros(m, device=prod.device, dtype=torch.float64).index_add_(0, rows, prod.abs_())
+    del prod, rows
+    return float(((y.double() - ref).abs() / scale.clamp_min(1e-300)).max())
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the reference's CSR5_avx2 backend on the host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, warmup, runs, sample_rows=None):
+    """Times oracle/_ref/libref_avx2.so (the reference's own CSR5_avx2, all host threads) on a bounded
+    sample of `workload`.  Returns dict(value GFLOPS, ms, cores, kind, sample, nnz)."""
+    import oracle
+    from benchmark_spmv_using_csr5_b200 import matrices as M
+    if workload == "c2":
+        rows = sample_rows or 2_500_000
+        A = M.banded(rows, 16)
+        val, x = M.values(A.nnz, A.n, "real", np.float64, 42)
+        sample = f"banded {rows} x {rows}, 16 nnz/row, FP64 ({A.nnz} nnz = 1/{10_000_000 // rows} of the workload's rows)"
+    elif workload == "c3":
+        A = M.rmat(18)
+        val, x = M.values(A.nnz, A.n, "real", np.float64, 42)
+        sample = f"R-MAT scale 18 ({A.nnz} nnz), FP64"
+    elif workload == "c4":
+        A, val = M.laplacian27(128)
+        val = val.astype(np.float32)
+        _, x = M.values(1, A.n, "real", np.float32, 42)
+        ms, _y, threads = oracle.ref_csr_omp_bench_f32(A.m, A.row_ptr, A.col, val, x, 0, warmup, runs)
+        return dict(value=2.0 * A.nnz / (ms * 1e6), ms=ms, cores=threads, kind="port", nnz=A.nnz,
+                    sample=f"27-pt Laplacian 128^3 FP32 ({A.nnz} nnz), OpenMP scalar CSR loop "
+                           "(the reference has no FP32 AVX2 path, README.md:36)")
+    else:
+        raise SystemExit(workload)
+    if not oracle.ref_available():
+        raise SystemExit("oracle/_ref/libref_avx2.so missing: run __graft_entry__.build() where /root/reference exists")
+    ms, conv_ms, y, threads = oracle.ref_avx2_bench(A.m, A.n, A.row_ptr, A.col, val, x, 0, warmup, runs)
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    ok = np.allclose(y, y_ref, rtol=1e-10, atol=0)
+    return dict(value=2.0 * A.nnz / (ms * 1e6), ms=ms, cores=threads, kind="reference", nnz=A.nnz,
+                sample=sample + f"; CSR5_avx2 sigma 16 omega 4; {warmup} warm-up + {runs} timed SpMVs"
+                                f"; y check vs scalar CSR: {'pass' if ok else 'FAIL'}; CSR->CSR5 {conv_ms:.1f} ms")
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    r = cpu_reference_run(args.workload, max(args.warmup, 1), max(args.steps, 1))
+    out = {
+        "impl": "reference",
+        "metric": "FP64 SpMV GFLOPS" if args.workload != "c4" else "FP32 SpMV GFLOPS",
+        "value": r["value"], "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if args.workload != "c4" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.time() - t0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto (= direct-load), 1 direct-load, 2 TMA-staged")
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--sigma", type=int, default=-1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from benchmark_spmv_using_csr5_b200 import handle as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE {world}; using WORLD_SIZE")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    w = build_workload(args.workload, torch, device, rank, world)
+    m, n, nnz, dtype = w["m"], w["n"], w["col"].numel(), w["dtype"]
+    vb = 8 if dtype == torch.float64 else 4
+
+    A = H.anonymouslibHandle(m, n, dtype)
+    assert A.inputCSR(nnz, w["row_ptr"], w["col"], w["val"]) == 0
+    assert A.setX(w["x"]) == 0
+    A.setSigma(args.sigma)
+    A.set_option(H.OPT_KERNEL, args.kernel)
+    A.set_option(H.OPT_TMA_STAGES, args.stages)
+    A.set_option(H.OPT_TMA_WARPS, args.warps)
+    A.set_option(H.OPT_CTAS_PER_SM, args.ctas_per_sm)
+    A.warmup()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    err = A.asCSR5()
+    torch.cuda.synchronize()
+    convert_ms = (time.perf_counter() - t0) * 1e3
+    assert err == 0, A.error_string(err)
+
+    y_full = torch.empty(m * world, device=device, dtype=dtype)   # concatenated y (all ranks' segments)
+    y = y_full[rank * m:(rank + 1) * m]
+
+    def step():
+        e = A.spmv(1.0, y)
+        if world > 1:
+            dist.all_gather_into_tensor(y_full, y)
+        return e
+
+    # one checked SpMV (the reference checks its first call, main.cu:80-82, 360-384)
+    assert step() == 0
+    torch.cuda.synchronize()
+    A.asCSR()  # the check needs col/val in CSR order; convert back afterwards
+    max_rel = exact_check(torch, w, y)
+    assert A.asCSR5() == 0
+    tol = 1e-6 if vb == 8 else 1e-4
+    assert max_rel <= tol, f"parity check failed: max rel err {max_rel}"
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    windows = []
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    A.kernel_times_ms()  # drop
+    A.set_option(H.OPT_KERNEL_TIMING, 1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    h0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync_all()
+    h1 = time.perf_counter()
+    windows.append((h0, h1))
+    ms_total = ev0.elapsed_time(ev1)
+    kt = A.kernel_times_ms()
+    A.set_option(H.OPT_KERNEL_TIMING, 0)
+    info = A.info()
+    launches_per_step = info.launches_per_spmv
+    if world > 1:
+        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    total_nnz = nnz
+    if world > 1:
+        t = torch.tensor([nnz], device=device, dtype=torch.int64)
+        dist.all_reduce(t)
+        total_nnz = int(t.item())
+    gflops = 2.0 * total_nnz / (ms_step * 1e6)
+
+    # ---- end to end through the host-buffer C-ABI call -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        x_host = w["x"].cpu().pin_memory()
+        y_host = torch.empty(m, dtype=dtype).pin_memory()
+        for _ in range(3):
+            assert A.spmv_host(1.0, x_host, y_host) == 0
+        e_steps = max(3, min(args.steps, 50))
+        sync_all()
+        g0 = time.perf_counter()
+        ev0.record()
+        for _ in range(e_steps):
+            A.spmv_host(1.0, x_host, y_host)
+        ev1.record()
+        sync_all()
+        g1 = time.perf_counter()
+        windows.append((g0, g1))
+        e_ms = ev0.elapsed_time(ev1) / e_steps
+        if world > 1:
+            t = torch.tensor([e_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        # carries of multi-tile rows are added with atomics: the last bits may differ between runs
+        assert torch.allclose(y_host.to(device), y, rtol=1e-12 if vb == 8 else 1e-5, atol=0), \
+            "host-buffer path disagrees with the device path"
+        e2e = {"value": 2.0 * total_nnz / (e_ms * 1e6), "unit": "GFLOP/s", "h2d_bytes_per_step": n * vb,
+               "d2h_bytes_per_step": m * vb, "ms_per_step": e_ms, "steps": e_steps,
+               "api": "csr5b200_spmv_host (pinned x H2D + SpMV + y D2H; CSR5 matrix resident)"}
+    sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    b_alg = algorithmic_bytes(m, n, nnz, vb)
+    k_ms = float(kt.mean()) if kt.size else ms_step
+    achieved = b_alg / (k_ms * 1e6)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "spmv_tma_kernel" if info.kernel_in_use == 2 else "spmv_direct_kernel",
+                "kernel_ms_avg": k_ms, "kernel_ms_min": float(kt.min()) if kt.size else None,
+                "kernel_launches_timed": int(kt.size), "algorithmic_bytes_per_launch": b_alg,
+                "bytes_per_nnz": b_alg / nnz, "peak_source": peak_src,
+                "roofline_gflops": 2.0 * nnz / (b_alg / (peak * 1e9)) / 1e9,
+                "whole_step_GBps": b_alg / (ms_step * 1e6),
+                "reference_getB_GBps": reference_getB(m, nnz, vb) / (ms_step * 1e6)}
+    traffic_path = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
+    if os.path.exists(traffic_path):  # dram bytes per launch from the committed ncu --set full capture
+        roofline["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(args.workload, 5, 30)
+        cpu = {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": r["sample"], "ms_per_spmv": r["ms"]}
+
+    out = {
+        "metric": "FP64 SpMV GFLOPS" if vb == 8 else "FP32 SpMV GFLOPS",
+        "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
+        "config": {
+            "workload": WORKLOADS[args.workload] + (f"; rank g owns rows [g*{m}, (g+1)*{m}) of the {n}-row matrix, "
+                                                    "x replicated, y all-gathered (NCCL) every step" if world > 1 else ""),
+            "m": m * world, "n": n, "nnz": total_nnz, "sigma": info.sigma, "omega": 32, "tiles_per_gpu": info.p,
+            "num_packet": info.num_packet, "values": "uniform (0,1], seed 42", "l2": "inputs larger than L2 "
+            f"({b_alg / 1e6:.0f} MB streamed per step vs 126 MB L2); no flush needed",
+            "kernel": roofline["kernel"], "launches_per_step": launches_per_step,
+            "csr_to_csr5_ms": convert_ms, "csr_to_csr5_in_spmvs": convert_ms / ms_step,
+            "parity_max_rel_err_vs_fp64_segment_sums": max_rel,
+        },
+        "clocks": sampler.summary(windows),
+        "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+    A.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

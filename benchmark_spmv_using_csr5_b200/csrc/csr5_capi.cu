@@ -248,12 +248,15 @@ int csr5b200_as_csr(csr5b200_handle_t h)
     return CSR5B200_SUCCESS;
 }
 
-int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y)
+static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void *const *y_dst)
 {
     if (!h) return CSR5B200_INVALID_ARGUMENT;
     if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_UNSUPPORTED_CSR_SPMV;
     if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
-    if (!y || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
+    if ((n_dst == 0 && !y) || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
+    if (n_dst < 0 || n_dst > CSR5B200_MAX_SCATTER || (n_dst > 0 && !y_dst)) return CSR5B200_INVALID_ARGUMENT;
+    for (int k = 0; k < n_dst; k++)
+        if (!y_dst[k]) return CSR5B200_INVALID_ARGUMENT;
     if (h->ignore_alpha) alpha = 1.0;
     cudaError_t e;
     h->tune.ev_begin = h->tune.ev_end = nullptr;
@@ -268,13 +271,21 @@ int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y)
         h->ev_used += 2;
     }
     if (h->pl.value_bytes == 8)
-        e = launch_spmv_f64(h->pl, h->tune, alpha, static_cast<double *>(y), h->stream, &h->kernel_in_use,
-                            &h->launches_per_spmv);
+        e = launch_spmv_f64(h->pl, h->tune, alpha, static_cast<double *>(y), n_dst, y_dst, h->stream,
+                            &h->kernel_in_use, &h->launches_per_spmv);
     else
-        e = launch_spmv_f32(h->pl, h->tune, (float)alpha, static_cast<float *>(y), h->stream,
+        e = launch_spmv_f32(h->pl, h->tune, (float)alpha, static_cast<float *>(y), n_dst, y_dst, h->stream,
                             &h->kernel_in_use, &h->launches_per_spmv);
     if (e != cudaSuccess) return cuda_fail(h, e);
     return CSR5B200_SUCCESS;
+}
+
+int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y) { return spmv_impl(h, alpha, y, 0, nullptr); }
+
+int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, int n_dst, void *const *y_dst)
+{
+    if (n_dst < 1) return CSR5B200_INVALID_ARGUMENT;
+    return spmv_impl(h, alpha, nullptr, n_dst, y_dst);
 }
 
 int csr5b200_destroy(csr5b200_handle_t h)

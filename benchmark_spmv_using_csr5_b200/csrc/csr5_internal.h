@@ -63,11 +63,13 @@ cudaError_t launch_transpose(const Plan &pl, bool r2c, cudaStream_t stream);
 cudaError_t launch_warmup(cudaStream_t stream);
 
 // ---- SpMV (csr5_spmv_f64.cu / csr5_spmv_f32.cu via csr5_spmv.cuh) -----------------------------
-// Enqueues [memset y] + compute(+tail) + calibrate.  Returns the kernel variant used in *used.
-cudaError_t launch_spmv_f64(const Plan &pl, const SpmvTuning &tn, double alpha, double *y,
-                            cudaStream_t stream, int *used, int *launches);
-cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y,
-                            cudaStream_t stream, int *used, int *launches);
+// Enqueues [clear y] + compute(+tail) + calibrate.  Returns the kernel variant used in *used.
+// n_dst == 0: y is the (local) result vector.  n_dst > 0: y is ignored and every value is stored to
+// y_dst[0..n_dst) instead (sharded mode: this rank's segment inside each peer's concatenated y).
+cudaError_t launch_spmv_f64(const Plan &pl, const SpmvTuning &tn, double alpha, double *y, int n_dst,
+                            void *const *y_dst, cudaStream_t stream, int *used, int *launches);
+cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, int n_dst,
+                            void *const *y_dst, cudaStream_t stream, int *used, int *launches);
 
 }  // namespace csr5
 

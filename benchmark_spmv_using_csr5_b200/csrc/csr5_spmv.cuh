@@ -54,7 +54,38 @@ struct SpmvArgs {
     int tail_start;      // first row of the tail tile
     int tail_nnz_start;  // (p - 1) * omega * sigma
     int tail_warps;      // ceil((m - tail_start) / 32)
+    // Sharded (multi-GPU) mode: every y value is stored to n_dst destination segments instead of y --
+    // this rank's slot in each peer's concatenated y, mapped over NVLink (csr5b200_spmv_scatter).
+    int n_dst;
+    VT *y_dst[CSR5B200_MAX_SCATTER];
 };
+
+// All y traffic of the kernels goes through these two helpers.  MULTI = false: the plain local
+// store / reduction.  MULTI = true: the store is replicated to every destination (fused all-gather:
+// peer stores ride NVLink while the tile stream keeps HBM busy).
+template <bool MULTI, typename VT>
+__device__ __forceinline__ void put_y(const SpmvArgs<VT> &a, int row, VT v)
+{
+    if constexpr (!MULTI) {
+        a.y[row] = v;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+            if (k < a.n_dst) a.y_dst[k][row] = v;
+    }
+}
+
+template <bool MULTI, typename VT>
+__device__ __forceinline__ void add_y(const SpmvArgs<VT> &a, int row, VT v)
+{
+    if constexpr (!MULTI) {
+        atomicAdd(a.y + row, v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+            if (k < a.n_dst) atomicAdd(a.y_dst[k] + row, v);  // red.global.add, also over NVLink
+    }
+}
 
 // ---- small device helpers ---------------------------------------------------------------------
 
@@ -102,7 +133,7 @@ struct SharedTile {  // TMA-staged kernel: conflict-free LDS (consecutive lanes,
 };
 
 // ---- one CSR5 tile (t < p - 1) ------------------------------------------------------------------
-template <typename VT, int SIGMA, typename Tile>
+template <typename VT, int SIGMA, bool MULTI, typename Tile>
 __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &tile, int t, int lane,
                                              uint32_t raw_start, uint32_t raw_stop)
 {
@@ -136,7 +167,7 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
         sum = warp_sum_xor<VT>(sum);
         if (lane == 0) {
             const bool starts_here = (tile.d(0, 0) >> (31 - a.bit_all)) & 1u;  // raw flag of element 0
-            if (starts_here) { a.y[row_start] = a.alpha * sum; a.cal[t] = (VT)0; }
+            if (starts_here) { put_y<MULTI, VT>(a, row_start, a.alpha * sum); a.cal[t] = (VT)0; }
             else a.cal[t] = a.alpha * sum;
         }
         return;
@@ -149,7 +180,7 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
     const uint32_t ff = f | (lane == 0 ? 1u : 0u);  // lane 0 always opens a segment (…:138)
     int y_idx = (int)(w0 >> (32 - a.bit_y));
     const int *__restrict__ yoff = dirty ? a.desc_off + a.desc_off_ptr[t] : nullptr;
-    VT *__restrict__ Y = a.y + row_start + 1;
+    const int Y = row_start + 1;  // rows stored by this tile are addressed relative to row_start + 1
 
     // `open`: the running segment began in this lane at a real row start, so it is stored
     // directly when it closes.  Lane 0's first segment (row_start itself) is handled at the end.
@@ -172,7 +203,7 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
             const int i = c0 + k;
             if (i < SIGMA) {
                 if (i > 0 && ((ff >> i) & 1u)) {
-                    if (open) { Y[dirty ? yoff[y_idx] : y_idx] = a.alpha * sum; y_idx++; }
+                    if (open) { put_y<MULTI, VT>(a, Y + (dirty ? yoff[y_idx] : y_idx), a.alpha * sum); y_idx++; }
                     else first_sum = sum;
                     open = true;
                     sum = 0;
@@ -200,16 +231,16 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
     }
     if (ff) last_sum += acc;
 
-    if (open) Y[dirty ? yoff[y_idx] : y_idx] = a.alpha * last_sum;
+    if (open) put_y<MULTI, VT>(a, Y + (dirty ? yoff[y_idx] : y_idx), a.alpha * last_sum);
     if (lane == 0) {
         const VT head = open ? first_sum : last_sum;  // lane 0's first segment = row_start's piece
-        if (f & 1u) { a.y[row_start] = a.alpha * head; a.cal[t] = (VT)0; }  // row starts on the tile boundary
+        if (f & 1u) { put_y<MULTI, VT>(a, row_start, a.alpha * head); a.cal[t] = (VT)0; }  // row starts on the tile boundary
         else a.cal[t] = a.alpha * head;                                      // carry-in from earlier tiles
     }
 }
 
 // ---- rows of the tail tile: 32 rows per warp, CSR-vector per non-empty row ----------------------
-template <typename VT>
+template <typename VT, bool MULTI>
 __device__ __forceinline__ void process_tail_rows(const SpmvArgs<VT> &a, int tw, int lane)
 {
     const int r = a.tail_start + tw * 32 + lane;
@@ -234,25 +265,25 @@ __device__ __forceinline__ void process_tail_rows(const SpmvArgs<VT> &a, int tw,
     if (r < a.m) {
         if (carried) a.cal[a.p - 1] = a.alpha * mine;
         else {
-            a.y[r] = a.alpha * mine;
+            put_y<MULTI, VT>(a, r, a.alpha * mine);
             if (r == a.tail_start) a.cal[a.p - 1] = (VT)0;
         }
     }
 }
 
 // ---- direct-load kernel ---------------------------------------------------------------------------
-template <typename VT, int SIGMA, int WPB>
+template <typename VT, int SIGMA, int WPB, bool MULTI>
 __global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT> a)
 {
     const int lane = threadIdx.x & 31;
     const long long unit = (long long)blockIdx.x * WPB + (threadIdx.x >> 5);
-    if (unit < a.tail_warps) { process_tail_rows<VT>(a, (int)unit, lane); return; }
+    if (unit < a.tail_warps) { process_tail_rows<VT, MULTI>(a, (int)unit, lane); return; }
     const long long tl = unit - a.tail_warps;
     if (tl >= a.p - 1) return;
     const int t = (int)tl;
     const size_t base = (size_t)t * (OMEGA * SIGMA);
     GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet};
-    process_tile<VT, SIGMA>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
+    process_tile<VT, SIGMA, MULTI>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
 }
 
 // ---- TMA-staged persistent kernel ---------------------------------------------------------------
@@ -326,7 +357,7 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
     __syncwarp();
 
     // tail rows first (they are few); warps stride over them
-    for (long long tw = gw; tw < a.tail_warps; tw += GW) process_tail_rows<VT>(a, (int)tw, lane);
+    for (long long tw = gw; tw < a.tail_warps; tw += GW) process_tail_rows<VT, false>(a, (int)tw, lane);
 
     const long long ntiles = a.p - 1;
     const uint32_t desc_bytes = OMEGA * 4 * a.num_packet;
@@ -365,7 +396,7 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
         SharedTile<VT> tile{reinterpret_cast<const VT *>(slot),
                             reinterpret_cast<const int *>(slot + Slot::VAL_BYTES),
                             reinterpret_cast<const uint32_t *>(slot + Slot::VAL_BYTES + Slot::COL_BYTES)};
-        process_tile<VT, SIGMA>(a, tile, (int)t, lane, raw_start, raw_stop);
+        process_tile<VT, SIGMA, false>(a, tile, (int)t, lane, raw_start, raw_stop);
 
         // this warp is done reading slot s: refill it with the tile `stages` iterations ahead
         __syncwarp();
@@ -381,14 +412,21 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
 }
 
 // ---- carries: y[row of tile t] += calibrator[t] for the tiles whose first row began earlier -----
-template <typename VT>
-__global__ void __launch_bounds__(256)
-calibrate_kernel(const uint32_t *__restrict__ tile_ptr, const VT *__restrict__ cal, VT *__restrict__ y, int p)
+template <typename VT, bool MULTI>
+__global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p) return;
-    const VT c = cal[t];
-    if (c != (VT)0) atomicAdd(y + (tile_ptr[t] & ROW_MASK), c);
+    if (t >= a.p) return;
+    const VT c = a.cal[t];
+    if (c != (VT)0) add_y<MULTI, VT>(a, (int)(a.tile_ptr[t] & ROW_MASK), c);
+}
+
+// sharded mode only: rows no tile stores (empty rows) are cleared in every destination
+template <typename VT>
+__global__ void __launch_bounds__(256) zero_rows_kernel(const SpmvArgs<VT> a)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.m; r += (long long)gridDim.x * blockDim.x)
+        put_y<true, VT>(a, (int)r, (VT)0);
 }
 
 // ---- host-side dispatch ----------------------------------------------------------------------------
@@ -398,9 +436,11 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
 {
     const long long ntiles = a.p - 1;
     int kernel = tn.kernel;
-    if (kernel == 0) kernel = tma_ok ? 2 : 1;
+    // auto = direct-load: on B200 it streams C2 at 98 % of the measured HBM copy bandwidth vs 87 % for
+    // the TMA-staged ring (profiles/r01_*; the ring's few, fat warps expose the x-gather latency).
+    if (kernel == 0) kernel = 1;
     if (kernel == 2 && !tma_ok) kernel = 1;
-    if (ntiles <= 0) kernel = 1;
+    if (ntiles <= 0 || a.n_dst > 0) kernel = 1;  // the scatter (sharded) variant exists for the direct kernel
     *used = kernel;
 
     if (kernel == 1) {
@@ -408,7 +448,8 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
         const long long units = ntiles + a.tail_warps;
         const long long blocks = (units + WPB - 1) / WPB;
         if (blocks <= 0) return cudaSuccess;
-        spmv_direct_kernel<VT, SIGMA, WPB><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
+        if (a.n_dst > 0) spmv_direct_kernel<VT, SIGMA, WPB, true><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
+        else spmv_direct_kernel<VT, SIGMA, WPB, false><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
         return cudaGetLastError();
     }
 
@@ -444,20 +485,30 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
 }
 
 template <typename VT>
-cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y, cudaStream_t stream,
-                          int *used, int *launches)
+cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y, int n_dst, void *const *y_dst,
+                          cudaStream_t stream, int *used, int *launches)
 {
     *used = 0;
     *launches = 0;
     if (pl.m <= 0) return cudaSuccess;
+    if (n_dst < 0 || n_dst > CSR5B200_MAX_SCATTER) return cudaErrorInvalidValue;
     cudaError_t e;
+    SpmvArgs<VT> a;
+    a.n_dst = n_dst;
+    for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) a.y_dst[k] = k < n_dst ? static_cast<VT *>(y_dst[k]) : nullptr;
+    a.m = pl.m;
     if (pl.needs_zero_fill || pl.p == 0) {
-        e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
+        if (n_dst > 0) {
+            a.y = nullptr;
+            zero_rows_kernel<VT><<<tn.num_sms * 8, 256, 0, stream>>>(a);
+            e = cudaGetLastError();
+        } else {
+            e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
+        }
         if (e != cudaSuccess) return e;
         ++*launches;
         if (pl.p == 0) return cudaSuccess;
     }
-    SpmvArgs<VT> a;
     a.row_ptr = pl.row_ptr;
     a.col = pl.col;
     a.val = static_cast<const VT *>(pl.val);
@@ -498,7 +549,8 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
     if (tn.ev_end && (e = cudaEventRecord(tn.ev_end, stream)) != cudaSuccess) return e;
     ++*launches;
     const int threads = 256;
-    calibrate_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a.tile_ptr, a.cal, y, pl.p);
+    if (n_dst > 0) calibrate_kernel<VT, true><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);
+    else calibrate_kernel<VT, false><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);
     ++*launches;
     return cudaGetLastError();
 }

@@ -84,6 +84,19 @@ CSR5B200_API int csr5b200_destroy(csr5b200_handle_t h);
 /* void setSigma(sigma | ANONYMOUSLIB_AUTO_TUNED_SIGMA)       anonymouslib_cuda.h:23, 294-318 */
 CSR5B200_API int csr5b200_set_sigma(csr5b200_handle_t h, int sigma);
 
+/* ---- multi-GPU (no reference counterpart: the reference is single-device) -------- */
+
+#define CSR5B200_MAX_SCATTER 8
+
+/* spmv() of a row-range shard whose result is written to n_dst destinations at once: y_dst[k] is the
+ * address of THIS shard's first row inside destination k's concatenated y (device pointers; peers'
+ * buffers mapped into this process over NVLink, e.g. CUDA IPC / symmetric memory; the local buffer is
+ * simply one of them).  Fuses the all-gather of the y segments into the SpMV kernels: finished rows
+ * are stored to every destination as tiles complete, carries use red.global.add on every destination.
+ * The caller synchronises the devices afterwards (a cross-GPU barrier) before anyone reads y.
+ * 1 <= n_dst <= CSR5B200_MAX_SCATTER.  Same return codes as spmv(). */
+CSR5B200_API int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, int n_dst, void *const *y_dst);
+
 /* Frees the handle object itself (the reference's handle is a stack object). Calls destroy(). */
 CSR5B200_API int csr5b200_free(csr5b200_handle_t h);
 
@@ -92,7 +105,7 @@ CSR5B200_API int csr5b200_free(csr5b200_handle_t h);
 /* Stream all later work of this handle is issued on (a cudaStream_t; NULL = legacy default). */
 CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
 
-#define CSR5B200_OPT_KERNEL        1  /* 0 auto (default), 1 direct-load kernel, 2 TMA-staged kernel */
+#define CSR5B200_OPT_KERNEL        1  /* 0 auto (default; = the faster one on B200: direct-load), 1 direct-load kernel, 2 TMA-staged kernel */
 #define CSR5B200_OPT_IGNORE_ALPHA  2  /* 1 = reference bug-compat: alpha treated as 1 */
 #define CSR5B200_OPT_TMA_STAGES    3  /* smem ring depth of the TMA-staged kernel (0 = default) */
 #define CSR5B200_OPT_TMA_WARPS     4  /* consumer warps per CTA of the TMA-staged kernel (0 = default) */

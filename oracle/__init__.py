@@ -9,7 +9,9 @@ Two libraries are wrapped with ctypes:
 * ``libcsr5_oracle.so``  -- plain-C restatement of the reference's CSR5_cuda algorithm
   (``oracle/csr5_oracle.c``; every function cites the reference file:line it follows);
 * ``_ref/libref_avx2.so`` -- the reference's OWN CSR5_avx2 backend compiled from
-  ``/root/reference/CSR5_avx2`` by ``oracle/Makefile`` (no reference source is copied).
+  ``/root/reference/CSR5_avx2`` by ``oracle/Makefile`` (no reference source is copied);
+* ``_ref/libref_cuda.so`` -- the reference's OWN CSR5_cuda backend, compiled for sm_100a from a
+  compat-patched scratch copy by ``oracle/build_ref_cuda.sh`` (needs a GPU to run).
 """
 from __future__ import annotations
 
@@ -101,6 +103,72 @@ def ref():
             [C.c_int] * 3 + [C.POINTER(C.c_double)]
         _ref = R
     return _ref
+
+
+_refcuda = None
+
+
+def ref_cuda_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_cuda.so"))
+
+
+def ref_cuda():
+    """The reference's own CSR5_cuda backend (``oracle/_ref/libref_cuda.so``); GPU required."""
+    global _refcuda
+    if _refcuda is None:
+        R = C.CDLL(os.path.join(_HERE, "_ref", "libref_cuda.so"))
+        for name, vp in (("f64", _f64p), ("f32", _f32p)):
+            f = getattr(R, f"ref_cuda_spmv_{name}")
+            f.argtypes = [C.c_int] * 3 + [_i32p, _i32p, vp, vp, vp, C.c_int, C.c_int, _i32p,
+                                          _u32p, C.c_size_t, _u32p, C.c_size_t, _i32p, C.c_size_t,
+                                          _i32p, C.c_size_t, _i32p, vp]
+            g = getattr(R, f"ref_cuda_bench_{name}")
+            g.argtypes = [C.c_int] * 3 + [_i32p, _i32p, vp, vp] + [C.c_int] * 3 + [C.POINTER(C.c_double)] * 2
+        _refcuda = R
+    return _refcuda
+
+
+def ref_cuda_spmv(m, n, row_ptr, col, val, x, sigma: int = -1, ncalls: int = 1) -> dict:
+    """Runs the reference's CSR5_cuda (inputCSR/setX/setSigma/asCSR5/spmv on zeroed y) and returns y
+    plus the CSR5 arrays its handle held.  Array capacities are sized from the CPU layout rules."""
+    val = np.ascontiguousarray(val)
+    name = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32"}[val.dtype]
+    nnz = len(col)
+    s = sigma if sigma > 0 else auto_sigma(m, nnz)
+    err, by, bs, npk, p = layout(s, nnz)
+    if err:
+        raise ValueError(err)
+    scal = np.zeros(8, np.int32)
+    tile_ptr = np.zeros(p + 1, np.uint32)
+    desc = np.zeros(max(p * OMEGA * npk, 1), np.uint32)
+    dop = np.zeros(p + 1, np.int32)
+    doff = np.zeros(m + p + 64, np.int32)
+    col5 = np.zeros(max(nnz, 1), np.int32)
+    val5 = np.zeros(max(nnz, 1), val.dtype)
+    y = np.zeros(m, val.dtype)
+    err = getattr(ref_cuda(), f"ref_cuda_spmv_{name}")(
+        m, n, nnz, np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col, np.int32), val,
+        np.ascontiguousarray(x, val.dtype), y, sigma, ncalls, scal, tile_ptr, tile_ptr.size, desc, desc.size,
+        dop, dop.size, doff, doff.size, col5, val5)
+    if err:
+        raise RuntimeError(f"reference CSR5_cuda returned {err}")
+    return {"y": y, "sigma": int(scal[0]), "bit_y": int(scal[1]), "bit_ss": int(scal[2]),
+            "num_packet": int(scal[3]), "p": int(scal[4]), "num_offsets": int(scal[5]),
+            "tail_start": int(scal[6]), "tile_ptr": tile_ptr, "desc": desc[:p * OMEGA * npk],
+            "desc_off_ptr": dop, "desc_off": doff[:int(scal[5])], "col5": col5[:nnz], "val5": val5[:nnz]}
+
+
+def ref_cuda_bench(m, n, row_ptr, col, val, x, sigma: int = -1, warmup: int = 50, runs: int = 1000):
+    """(ms per SpMV, conversion ms) of the reference's CSR5_cuda with the protocol of main.cu:79-106."""
+    val = np.ascontiguousarray(val)
+    name = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32"}[val.dtype]
+    ms, conv = C.c_double(0), C.c_double(0)
+    err = getattr(ref_cuda(), f"ref_cuda_bench_{name}")(
+        m, n, len(col), np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col, np.int32), val,
+        np.ascontiguousarray(x, val.dtype), sigma, warmup, runs, C.byref(ms), C.byref(conv))
+    if err:
+        raise RuntimeError(f"reference CSR5_cuda returned {err}")
+    return ms.value, conv.value
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,80 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/csr5_b200.h declares, and the host-side argument checks / error paths that need no GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from benchmark_spmv_using_csr5_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "csr5_b200.h")).read()
+    return sorted(set(re.findall(r"CSR5B200_API\s+[\w\s\*]+?\b(csr5b200_\w+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    _lib.build_library()
+    lib = _lib.load_library()
+    assert lib.csr5b200_version().decode().startswith("csr5-b200")
+
+
+def test_every_declared_symbol_is_exported_and_typed():
+    lib = _lib.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/csr5_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.SIGNATURES"
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_error_strings_and_codes():
+    lib = _lib.load_library()
+    # detail/common.h:13-18
+    assert b"success" in lib.csr5b200_error_string(0)
+    for code in (-1, -2, -3, -4, -5, -100, -101):
+        assert lib.csr5b200_error_string(code)
+    assert lib.csr5b200_create(4, 4, 2, C.byref(C.c_void_p())) == -5     # UNSUPPORTED_VALUE_TYPE
+    assert lib.csr5b200_create(-1, 4, 8, C.byref(C.c_void_p())) == -101
+    assert lib.csr5b200_spmv(None, 1.0, None) == -101
+
+
+def test_handle_state_machine_without_gpu():
+    """Call-order rules of anonymouslib_cuda.h that are decided on the host."""
+    lib = _lib.load_library()
+    h = C.c_void_p()
+    assert lib.csr5b200_create(10, 10, 8, C.byref(h)) == 0
+    assert lib.csr5b200_as_csr5(h) == -1                 # UNKOWN_FORMAT: inputCSR not called
+    assert lib.csr5b200_spmv(h, 1.0, C.c_void_p(16)) == -1
+    assert lib.csr5b200_input_csr(h, 30, None, None, None) == 0
+    assert lib.csr5b200_spmv(h, 1.0, C.c_void_p(16)) == -4   # UNSUPPORTED_CSR_SPMV (anonymouslib_cuda.h:266-269)
+    info = _lib.Csr5Info()
+    assert lib.csr5b200_set_sigma(h, -1) == 0
+    assert lib.csr5b200_get_info(h, C.byref(info)) == 0
+    assert (info.m, info.n, info.nnz, info.sigma, info.format) == (10, 10, 30, 4, 0)   # 30 / 10 = 3 <= 4 -> 4
+    assert lib.csr5b200_set_sigma(h, 3) == 0
+    assert lib.csr5b200_as_csr5(h) == -3                 # CSR_TO_CSR5_FAILED: sigma outside [4, 32]
+    assert lib.csr5b200_set_option(h, 99, 0) == -101
+    assert lib.csr5b200_as_csr(h) == 0
+    assert lib.csr5b200_free(h) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.Csr5LibraryMissing):
+        _lib.load_library()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "benchmark_spmv_using_csr5_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, re.M), f
+                assert "csr5_oracle" not in txt and "libref_" not in txt, f

@@ -247,6 +247,10 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--sigma", type=int, default=-1)
+    ap.add_argument("--wpb", type=int, default=0, help="tuning: warps per CTA of the direct kernel")
+    ap.add_argument("--nch", type=int, default=0, help="tuning: register chunks per tile")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: y exchange fused into the SpMV kernels (peer stores) or NCCL all-gather after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -272,30 +276,33 @@ def main():
     m, n, nnz, dtype = w["m"], w["n"], w["col"].numel(), w["dtype"]
     vb = 8 if dtype == torch.float64 else 4
 
-    A = H.anonymouslibHandle(m, n, dtype)
-    assert A.inputCSR(nnz, w["row_ptr"], w["col"], w["val"]) == 0
-    assert A.setX(w["x"]) == 0
-    A.setSigma(args.sigma)
+    from benchmark_spmv_using_csr5_b200 import sharded as S
+    bounds = np.arange(world + 1, dtype=np.int64) * m   # weak scaling: equal row ranges
+    mode = args.exchange if world > 1 else "local"
+    sh = S.ShardedCsr5(bounds, n, w["row_ptr"], w["col"], w["val"], mode="fused" if mode == "fused" else "nccl",
+                       sigma=args.sigma)
+    A = sh.h   # the ordinary single-GPU handle of this rank's rows
+    assert sh.setX(w["x"]) == 0
     A.set_option(H.OPT_KERNEL, args.kernel)
     A.set_option(H.OPT_TMA_STAGES, args.stages)
     A.set_option(H.OPT_TMA_WARPS, args.warps)
     A.set_option(H.OPT_CTAS_PER_SM, args.ctas_per_sm)
+    A.set_option(H.OPT_DIRECT_WPB, args.wpb)
+    A.set_option(H.OPT_DIRECT_NCH, args.nch)
     A.warmup()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    err = A.asCSR5()
+    err = sh.asCSR5()
     torch.cuda.synchronize()
     convert_ms = (time.perf_counter() - t0) * 1e3
     assert err == 0, A.error_string(err)
 
-    y_full = torch.empty(m * world, device=device, dtype=dtype)   # concatenated y (all ranks' segments)
-    y = y_full[rank * m:(rank + 1) * m]
+    y_full = sh.y_full   # concatenated y (all ranks' segments)
+    y = sh.y_local
 
     def step():
-        e = A.spmv(1.0, y)
-        if world > 1:
-            dist.all_gather_into_tensor(y_full, y)
-        return e
+        sh.spmv(1.0)
+        return 0
 
     # one checked SpMV (the reference checks its first call, main.cu:80-82, 360-384)
     assert step() == 0
@@ -305,6 +312,13 @@ def main():
     assert A.asCSR5() == 0
     tol = 1e-6 if vb == 8 else 1e-4
     assert max_rel <= tol, f"parity check failed: max rel err {max_rel}"
+
+    if world > 1:
+        # every rank must hold the same concatenated y: compare a checksum of all segments
+        cs = y_full.double().sum().reshape(1)
+        allcs = [torch.empty_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        assert all(torch.allclose(c, allcs[0], rtol=1e-12) for c in allcs), "ranks disagree on the gathered y"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -316,31 +330,38 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def time_loop(fn, warmup, steps):
+        """W untimed + K timed calls of fn between two events on the current stream, bracketed by
+        device sync + barrier; returns ms per step, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        h0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        sync_all()
+        windows.append((h0, time.perf_counter()))
+        ms = ev0.elapsed_time(ev1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     # ---- device-resident timing -------------------------------------------------------------
     for _ in range(args.warmup):
         step()
     A.kernel_times_ms()  # drop
     A.set_option(H.OPT_KERNEL_TIMING, 1)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    h0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    h1 = time.perf_counter()
-    windows.append((h0, h1))
-    ms_total = ev0.elapsed_time(ev1)
+    ms_step = time_loop(step, 0, args.steps)
     kt = A.kernel_times_ms()
     A.set_option(H.OPT_KERNEL_TIMING, 0)
     info = A.info()
     launches_per_step = info.launches_per_spmv
-    if world > 1:
-        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
     total_nnz = nnz
     if world > 1:
         t = torch.tensor([nnz], device=device, dtype=torch.int64)
@@ -348,34 +369,50 @@ def main():
         total_nnz = int(t.item())
     gflops = 2.0 * total_nnz / (ms_step * 1e6)
 
+    multi = None
+    if world > 1:
+        # the same step with the exchange done the other way, and without any exchange
+        k2 = max(3, min(args.steps, 200))
+        ms_local = time_loop(lambda: sh.spmv_local(1.0), 3, k2)
+
+        def nccl_step():
+            sh.spmv_local(1.0)
+            S.allgather_v(y_full, bounds, rank)
+        ms_nccl = time_loop(nccl_step, 3, k2)
+        link_gbs = 770.0  # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)
+        in_bytes = (world - 1) * m * vb
+        t_link = in_bytes / (link_gbs * 1e6)
+        multi = {"exchange": mode, "ms_per_step_spmv_only_no_exchange": ms_local,
+                 "ms_per_step_spmv_then_nccl_allgather": ms_nccl, "ms_per_step_fused_peer_stores": ms_step
+                 if mode == "fused" else None,
+                 "nvlink_inbound_bytes_per_gpu_per_step": in_bytes, "nvlink_peak_GBps_per_direction": link_gbs,
+                 "nvlink_time_floor_ms": t_link,
+                 "note": "every rank ends each step holding all of y: (N-1)*m*sizeof(VT) bytes must enter each "
+                         "GPU over NVLink per step, which bounds the step from below next to the HBM stream"}
+
     # ---- end to end through the host-buffer C-ABI call -----------------------------------------
     e2e = None
     if not args.no_e2e:
         x_host = w["x"].cpu().pin_memory()
         y_host = torch.empty(m, dtype=dtype).pin_memory()
-        for _ in range(3):
-            assert A.spmv_host(1.0, x_host, y_host) == 0
+        if world == 1:
+            def e2e_step():
+                assert A.spmv_host(1.0, x_host, y_host) == 0
+            api = "csr5b200_spmv_host (pinned x H2D + SpMV + y D2H; CSR5 matrix resident)"
+        else:
+            def e2e_step():   # every rank: upload the replicated x, sharded SpMV + exchange, download its rows
+                w["x"].copy_(x_host, non_blocking=True)
+                sh.spmv(1.0)
+                y_host.copy_(y, non_blocking=True)
+            api = "ShardedCsr5.spmv (per rank: pinned x H2D, SpMV + y exchange, D2H of the rank's y rows)"
         e_steps = max(3, min(args.steps, 50))
-        sync_all()
-        g0 = time.perf_counter()
-        ev0.record()
-        for _ in range(e_steps):
-            A.spmv_host(1.0, x_host, y_host)
-        ev1.record()
-        sync_all()
-        g1 = time.perf_counter()
-        windows.append((g0, g1))
-        e_ms = ev0.elapsed_time(ev1) / e_steps
-        if world > 1:
-            t = torch.tensor([e_ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
+        e_ms = time_loop(e2e_step, 3, e_steps)
+        torch.cuda.synchronize()
         # carries of multi-tile rows are added with atomics: the last bits may differ between runs
         assert torch.allclose(y_host.to(device), y, rtol=1e-12 if vb == 8 else 1e-5, atol=0), \
             "host-buffer path disagrees with the device path"
         e2e = {"value": 2.0 * total_nnz / (e_ms * 1e6), "unit": "GFLOP/s", "h2d_bytes_per_step": n * vb,
-               "d2h_bytes_per_step": m * vb, "ms_per_step": e_ms, "steps": e_steps,
-               "api": "csr5b200_spmv_host (pinned x H2D + SpMV + y D2H; CSR5 matrix resident)"}
+               "d2h_bytes_per_step": m * vb, "ms_per_step": e_ms, "steps": e_steps, "api": api}
     sampler.stop()
 
     if rank != 0:
@@ -417,7 +454,7 @@ def main():
         "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
         "config": {
             "workload": WORKLOADS[args.workload] + (f"; rank g owns rows [g*{m}, (g+1)*{m}) of the {n}-row matrix, "
-                                                    "x replicated, y all-gathered (NCCL) every step" if world > 1 else ""),
+                                                    f"x replicated, y concatenated on every rank each step ({mode})" if world > 1 else ""),
             "m": m * world, "n": n, "nnz": total_nnz, "sigma": info.sigma, "omega": 32, "tiles_per_gpu": info.p,
             "num_packet": info.num_packet, "values": "uniform (0,1], seed 42", "l2": "inputs larger than L2 "
             f"({b_alg / 1e6:.0f} MB streamed per step vs 126 MB L2); no flush needed",
@@ -430,6 +467,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "multi_gpu": multi,
     }
     print(json.dumps(out), flush=True)
     A.free()

@@ -147,6 +147,8 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_TMA_WARPS: h->tune.tma_warps = value; break;
         case CSR5B200_OPT_CTAS_PER_SM: h->tune.ctas_per_sm = value; break;
         case CSR5B200_OPT_KERNEL_TIMING: h->kernel_timing = value != 0; break;
+        case CSR5B200_OPT_DIRECT_WPB: h->tune.direct_wpb = value; break;
+        case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
         default: return CSR5B200_INVALID_ARGUMENT;
     }
     return CSR5B200_SUCCESS;

@@ -46,6 +46,8 @@ struct SpmvTuning {
     int tma_warps = 0;
     int ctas_per_sm = 0;
     int num_sms = 148;
+    int direct_wpb = 0;    // tuning: warps per CTA of the direct kernel (0 = default 4)
+    int direct_nch = 0;    // tuning: register chunks per tile (0 = default rule)
     cudaEvent_t ev_begin = nullptr;  // optional: recorded right before / after the main SpMV kernel
     cudaEvent_t ev_end = nullptr;
 };

@@ -133,13 +133,19 @@ struct SharedTile {  // TMA-staged kernel: conflict-free LDS (consecutive lanes,
 };
 
 // ---- one CSR5 tile (t < p - 1) ------------------------------------------------------------------
-template <typename VT, int SIGMA, bool MULTI, typename Tile>
+// number of register chunks a tile's sigma elements are consumed in (0 = default rule)
+template <int SIGMA, int NCH> struct ChunkOf {
+    static constexpr int N = NCH > 0 ? NCH : (SIGMA <= 16 ? 1 : 2);
+    static constexpr int CH = (SIGMA + N - 1) / N;
+};
+
+template <typename VT, int SIGMA, bool MULTI, typename Tile, int NCH = 0>
 __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &tile, int t, int lane,
                                              uint32_t raw_start, uint32_t raw_stop)
 {
     // Elements are consumed in register chunks so that all streaming loads and x gathers of a chunk
     // are in flight together without spilling at sigma = 32.
-    constexpr int CH = SIGMA <= 16 ? SIGMA : (SIGMA + 1) / 2;
+    constexpr int CH = ChunkOf<SIGMA, NCH>::CH;
     const int row_start = (int)(raw_start & ROW_MASK);
     const int row_stop = (int)(raw_stop & ROW_MASK);
     const VT *__restrict__ x = a.x;
@@ -272,7 +278,7 @@ __device__ __forceinline__ void process_tail_rows(const SpmvArgs<VT> &a, int tw,
 }
 
 // ---- direct-load kernel ---------------------------------------------------------------------------
-template <typename VT, int SIGMA, int WPB, bool MULTI>
+template <typename VT, int SIGMA, int WPB, bool MULTI, int NCH = 0>
 __global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT> a)
 {
     const int lane = threadIdx.x & 31;
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT
     const int t = (int)tl;
     const size_t base = (size_t)t * (OMEGA * SIGMA);
     GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet};
-    process_tile<VT, SIGMA, MULTI>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
+    process_tile<VT, SIGMA, MULTI, GlobalTile<VT>, NCH>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
 }
 
 // ---- TMA-staged persistent kernel ---------------------------------------------------------------
@@ -444,10 +450,27 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
     *used = kernel;
 
     if (kernel == 1) {
-        constexpr int WPB = 4;
         const long long units = ntiles + a.tail_warps;
+        if (units <= 0) return cudaSuccess;
+        // tuning variants (CSR5B200_OPT_DIRECT_WPB / _NCH), instantiated for the sigmas of the benchmark
+        // configurations only; everything else uses the default shape
+        if constexpr (SIGMA == 15 || SIGMA == 16 || SIGMA == 26) {
+            if (a.n_dst == 0 && (tn.direct_wpb > 0 || tn.direct_nch > 0)) {
+                const int wpb = tn.direct_wpb > 0 ? tn.direct_wpb : 4;
+                const int nch = tn.direct_nch > 0 ? tn.direct_nch : ChunkOf<SIGMA, 0>::N;
+#define CSR5_VARIANT(W, N)                                                                                   \
+    if (wpb == W && nch == N) {                                                                              \
+        spmv_direct_kernel<VT, SIGMA, W, false, N><<<(unsigned)((units + W - 1) / W), W * 32, 0, stream>>>(a); \
+        return cudaGetLastError();                                                                           \
+    }
+                CSR5_VARIANT(2, 1) CSR5_VARIANT(2, 2) CSR5_VARIANT(4, 1) CSR5_VARIANT(4, 2) CSR5_VARIANT(8, 1)
+                CSR5_VARIANT(8, 2) CSR5_VARIANT(16, 1) CSR5_VARIANT(16, 2) CSR5_VARIANT(4, 3) CSR5_VARIANT(8, 3)
+#undef CSR5_VARIANT
+                return cudaErrorInvalidValue;
+            }
+        }
+        constexpr int WPB = 4;
         const long long blocks = (units + WPB - 1) / WPB;
-        if (blocks <= 0) return cudaSuccess;
         if (a.n_dst > 0) spmv_direct_kernel<VT, SIGMA, WPB, true><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
         else spmv_direct_kernel<VT, SIGMA, WPB, false><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
         return cudaGetLastError();

@@ -43,6 +43,8 @@ OPT_TMA_STAGES = 3
 OPT_TMA_WARPS = 4
 OPT_CTAS_PER_SM = 5
 OPT_KERNEL_TIMING = 6
+OPT_DIRECT_WPB = 7
+OPT_DIRECT_NCH = 8
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
 
 
@@ -111,6 +113,13 @@ class anonymouslibHandle:
         _check_dev(y, self.dtype, "y", self.m)
         self._bind_stream()
         return self._lib.csr5b200_spmv(self._h, float(alpha), _ptr(y))
+
+    def spmv_scatter(self, alpha: float, y_dst, n_dst: int) -> int:
+        """Sharded mode: ``y_dst`` is a ctypes array of ``n_dst`` device pointers, each the address of
+        this shard's first row inside one destination's concatenated y (csr5b200_spmv_scatter)."""
+        self._bind_stream()
+        return self._lib.csr5b200_spmv_scatter(self._h, float(alpha), int(n_dst),
+                                               C.cast(y_dst, C.POINTER(C.c_void_p)))
 
     def destroy(self) -> int:
         if not self._h:

@@ -112,6 +112,8 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
 #define CSR5B200_OPT_CTAS_PER_SM   5  /* persistent-grid size factor (0 = default) */
 #define CSR5B200_OPT_KERNEL_TIMING 6  /* 1 = bracket the main SpMV kernel of every spmv() with CUDA events
                                          (see csr5b200_get_kernel_times); 0 = off (default) */
+#define CSR5B200_OPT_DIRECT_WPB    7  /* tuning: warps per CTA of the direct kernel (2/4/8/16; 0 = default) */
+#define CSR5B200_OPT_DIRECT_NCH    8  /* tuning: register chunks per tile (1/2/3; 0 = default rule) */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays

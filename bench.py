@@ -247,6 +247,8 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--sigma", type=int, default=-1)
+    ap.add_argument("--hot", type=int, default=0, help="hot-column table: 0 off (default), -1 auto, K entries")
+    ap.add_argument("--hot-threads", type=int, default=0)
     ap.add_argument("--wpb", type=int, default=0, help="tuning: warps per CTA of the direct kernel")
     ap.add_argument("--nch", type=int, default=0, help="tuning: register chunks per tile")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -287,6 +289,8 @@ def main():
     A.set_option(H.OPT_TMA_STAGES, args.stages)
     A.set_option(H.OPT_TMA_WARPS, args.warps)
     A.set_option(H.OPT_CTAS_PER_SM, args.ctas_per_sm)
+    A.set_option(H.OPT_HOT_COLUMNS, args.hot)
+    A.set_option(H.OPT_HOT_THREADS, args.hot_threads)
     A.set_option(H.OPT_DIRECT_WPB, args.wpb)
     A.set_option(H.OPT_DIRECT_NCH, args.nch)
     A.warmup()
@@ -395,24 +399,52 @@ def main():
     if not args.no_e2e:
         x_host = w["x"].cpu().pin_memory()
         y_host = torch.empty(m, dtype=dtype).pin_memory()
+        e2e_sync_ms = None
         if world == 1:
             def e2e_step():
                 assert A.spmv_host(1.0, x_host, y_host) == 0
-            api = "csr5b200_spmv_host (pinned x H2D + SpMV + y D2H; CSR5 matrix resident)"
+            e2e_sync_ms = time_loop(e2e_step, 3, 20)   # one synchronous call per step, nothing overlapped
+            assert torch.allclose(y_host.to(device), y, rtol=1e-12 if vb == 8 else 1e-5, atol=0)
+            # the headline e2e: a stream of independent SpMVs through the pipelined host-buffer call; every
+            # step still uploads its own x and downloads its own y (4 rotating pinned buffer pairs)
+            nbuf = 4
+            xs_host = [x_host] + [x_host.clone().pin_memory() for _ in range(nbuf - 1)]
+            ys_host = [y_host] + [torch.empty(m, dtype=dtype).pin_memory() for _ in range(nbuf - 1)]
+            e_batch = max(3, min(args.steps, 50))
+
+            def e2e_step():
+                assert A.spmv_host_batch(1.0, [xs_host[i % nbuf] for i in range(e_batch)],
+                                         [ys_host[i % nbuf] for i in range(e_batch)]) == 0
+            ms_batch = time_loop(e2e_step, 1, 2)
+            api = (f"csr5b200_spmv_host_batch: {e_batch} independent SpMVs per call, each with its own pinned x H2D and "
+                   "y D2H, software-pipelined (upload k+1 | SpMV k | download k-1); CSR5 matrix resident")
         else:
-            def e2e_step():   # every rank: upload the replicated x, sharded SpMV + exchange, download its rows
-                w["x"].copy_(x_host, non_blocking=True)
+            x_dev = w["x"]
+            x_slice_dev = x_dev[rank * m:(rank + 1) * m]           # n = world * m: rank g uploads x[g*m:(g+1)*m]
+            x_slice_host = x_host[rank * m:(rank + 1) * m]
+
+            def e2e_step():   # every rank: upload ITS slice of x over PCIe, replicate x over NVLink (NCCL
+                #               all-gather), sharded SpMV + fused y exchange, download its rows of y
+                x_slice_dev.copy_(x_slice_host, non_blocking=True)
+                dist.all_gather_into_tensor(x_dev, x_slice_dev)
                 sh.spmv(1.0)
                 y_host.copy_(y, non_blocking=True)
-            api = "ShardedCsr5.spmv (per rank: pinned x H2D, SpMV + y exchange, D2H of the rank's y rows)"
-        e_steps = max(3, min(args.steps, 50))
-        e_ms = time_loop(e2e_step, 3, e_steps)
+            api = ("per rank: pinned H2D of its 1/N slice of x, NCCL all-gather of x, ShardedCsr5.spmv (SpMV + y "
+                   "exchange), D2H of the rank's y rows; bytes are whole-job totals")
+        if world == 1:
+            e_steps, e_ms = 2 * e_batch, ms_batch / e_batch
+            for yh in ys_host:
+                assert torch.allclose(yh.to(device), y, rtol=1e-12 if vb == 8 else 1e-5, atol=0)
+        else:
+            e_steps = max(3, min(args.steps, 50))
+            e_ms = time_loop(e2e_step, 3, e_steps)
         torch.cuda.synchronize()
         # carries of multi-tile rows are added with atomics: the last bits may differ between runs
         assert torch.allclose(y_host.to(device), y, rtol=1e-12 if vb == 8 else 1e-5, atol=0), \
             "host-buffer path disagrees with the device path"
         e2e = {"value": 2.0 * total_nnz / (e_ms * 1e6), "unit": "GFLOP/s", "h2d_bytes_per_step": n * vb,
-               "d2h_bytes_per_step": m * vb, "ms_per_step": e_ms, "steps": e_steps, "api": api}
+               "d2h_bytes_per_step": m * world * vb, "ms_per_step": e_ms, "steps": e_steps, "api": api,
+               "ms_per_step_unpipelined_single_call": e2e_sync_ms}
     sampler.stop()
 
     if rank != 0:
@@ -430,7 +462,7 @@ def main():
     k_ms = float(kt.mean()) if kt.size else ms_step
     achieved = b_alg / (k_ms * 1e6)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "spmv_tma_kernel" if info.kernel_in_use == 2 else "spmv_direct_kernel",
+                "traffic": None, "kernel": {1: "spmv_direct_kernel", 2: "spmv_tma_kernel", 3: "spmv_hot_kernel"}.get(info.kernel_in_use, "?"),
                 "kernel_ms_avg": k_ms, "kernel_ms_min": float(kt.min()) if kt.size else None,
                 "kernel_launches_timed": int(kt.size), "algorithmic_bytes_per_launch": b_alg,
                 "bytes_per_nnz": b_alg / nnz, "peak_source": peak_src,
@@ -459,6 +491,7 @@ def main():
             "num_packet": info.num_packet, "values": "uniform (0,1], seed 42", "l2": "inputs larger than L2 "
             f"({b_alg / 1e6:.0f} MB streamed per step vs 126 MB L2); no flush needed",
             "kernel": roofline["kernel"], "launches_per_step": launches_per_step,
+            "hot_columns": info.hot_columns, "hot_coverage": info.hot_coverage,
             "csr_to_csr5_ms": convert_ms, "csr_to_csr5_in_spmvs": convert_ms / ms_step,
             "parity_max_rel_err_vs_fp64_segment_sums": max_rel,
         },

@@ -30,6 +30,7 @@ class Csr5Info(C.Structure):
         ("partition_descriptor_offset_pointer", C.c_void_p),
         ("partition_descriptor_offset", C.c_void_p), ("calibrator", C.c_void_p),
         ("last_cuda_error", C.c_int), ("launches_per_spmv", C.c_int),
+        ("hot_columns", C.c_int), ("hot_coverage", C.c_double),
     ]
 
 
@@ -52,6 +53,8 @@ SIGNATURES = {
     "csr5b200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
     "csr5b200_copy_meta_to_host": (C.c_int, [C.c_void_p] * 6),
     "csr5b200_spmv_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "csr5b200_spmv_host_batch": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p)]),
     "csr5b200_call_anonymouslib": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                               C.c_int, C.c_int]),

@@ -22,6 +22,10 @@ struct csr5b200_handle_s {
     int launches_per_spmv = 0;
     void *x_stage = nullptr;  // device staging for spmv_host
     void *y_stage = nullptr;
+    // spmv_host_batch pipeline: double-buffered staging, copy streams, events
+    void *xb[2] = {nullptr, nullptr}, *yb[2] = {nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     int kernel_timing = 0;
     std::vector<cudaEvent_t> ev;  // begin/end pairs of the timed main kernels
     size_t ev_used = 0;           // events recorded since the last get_kernel_times()
@@ -50,6 +54,12 @@ void release_csr5_arrays(csr5b200_handle_t h)
     cudaFree(pl.desc_off);
     cudaFree(pl.calibrator);
     cudaFree(pl.dev_flags);
+    cudaFree(pl.hot_col);
+    cudaFree(pl.hot_x);
+    pl.hot_col = nullptr;
+    pl.hot_x = nullptr;
+    pl.hot_k = 0;
+    pl.hot_coverage = 0.0;
     pl.tile_ptr = nullptr;
     pl.desc = nullptr;
     pl.desc_off_ptr = nullptr;
@@ -68,6 +78,72 @@ int auto_sigma(int m, int nnz)
     if (k <= 32) return k;
     if (k <= 256) return 32;
     return 6;
+}
+
+// Hot-column table: pick the most referenced columns of the CSR5 tiles, at most
+// `capacity`, by bisecting the reference-count threshold; tag their occurrences in col (bit 31 | slot).
+// Auto mode keeps the table only when it would serve >= 25 % of the tiles' x references.
+int build_hot_table(csr5b200_handle_t h)
+{
+    Plan &pl = h->pl;
+    const int mode = h->tune.hot_columns;
+    if (mode == 0 || pl.p < 2 || pl.n <= 0) return CSR5B200_SUCCESS;
+    const size_t vb = (size_t)pl.value_bytes;
+    int capacity = mode > 0 ? mode : (int)((128 * 1024) / vb);   // auto: 128 KB of shared memory
+    const int cap_max = (int)((200 * 1024) / vb);
+    if (capacity > cap_max) capacity = cap_max;
+    const long long limit = (long long)(pl.p - 1) * OMEGA * pl.sigma;
+    int *cnt = nullptr, *slot = nullptr;
+    unsigned long long *out2 = nullptr;
+    void *scratch = nullptr;
+    const size_t scratch_bytes = scan_scratch_bytes(pl.n);
+    auto done = [&](int code) {
+        cudaFree(cnt); cudaFree(slot); cudaFree(out2); cudaFree(scratch);
+        return code;
+    };
+#define CUH(call)                                                   \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return done(cuda_fail(h, e__));     \
+    } while (0)
+    CUH(cudaMalloc(&cnt, (size_t)pl.n * sizeof(int)));
+    CUH(cudaMalloc(&out2, 2 * sizeof(unsigned long long)));
+    CUH(cudaMemsetAsync(cnt, 0, (size_t)pl.n * sizeof(int), h->stream));
+    CUH(launch_hot_count(pl.col, limit, cnt, h->tune.num_sms, h->stream));
+    // smallest threshold whose column set fits the table (set size is non-increasing in the threshold)
+    unsigned long long res[2] = {0, 0};
+    auto count_ge = [&](long long thr) -> cudaError_t {
+        cudaError_t e = launch_hot_count_ge(cnt, pl.n, (int)thr, out2, h->tune.num_sms, h->stream);
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(res, out2, sizeof(res), cudaMemcpyDeviceToHost, h->stream);
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(h->stream);
+    };
+    long long lo = 1, hi = limit + 1;   // invariant: set(hi) fits; set(lo - 1) does not (or lo == 1)
+    while (lo < hi) {
+        const long long mid = lo + (hi - lo) / 2;
+        CUH(count_ge(mid));
+        if (res[0] <= (unsigned long long)capacity) hi = mid; else lo = mid + 1;
+    }
+    CUH(count_ge(lo));
+    const int threshold = (int)lo;
+    const int hot_k = (int)res[0];
+    const double coverage = limit > 0 ? (double)res[1] / (double)limit : 0.0;
+    if (hot_k <= 0 || (mode < 0 && coverage < 0.25)) return done(CSR5B200_SUCCESS);
+
+    CUH(cudaMalloc(&slot, (size_t)(pl.n + 1) * sizeof(int)));
+    CUH(cudaMalloc(&scratch, scratch_bytes));
+    CUH(cudaMalloc(&pl.hot_col, (size_t)hot_k * sizeof(int)));
+    CUH(cudaMalloc(&pl.hot_x, ((size_t)hot_k * vb + 15) / 16 * 16));
+    CUH(cudaMemsetAsync(pl.hot_x, 0, ((size_t)hot_k * vb + 15) / 16 * 16, h->stream));
+    CUH(launch_hot_flags(cnt, pl.n, threshold, slot, h->stream));
+    CUH(launch_exclusive_scan(slot, pl.n + 1, scratch, scratch_bytes, h->stream));
+    CUH(launch_hot_assign(cnt, pl.n, threshold, slot, pl.hot_col, pl.col, limit, h->tune.num_sms, h->stream));
+    CUH(cudaStreamSynchronize(h->stream));
+#undef CUH
+    pl.hot_k = hot_k;
+    pl.hot_coverage = coverage;
+    return done(CSR5B200_SUCCESS);
 }
 
 }  // namespace
@@ -149,6 +225,8 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_KERNEL_TIMING: h->kernel_timing = value != 0; break;
         case CSR5B200_OPT_DIRECT_WPB: h->tune.direct_wpb = value; break;
         case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
+        case CSR5B200_OPT_HOT_COLUMNS: h->tune.hot_columns = value; break;
+        case CSR5B200_OPT_HOT_THREADS: h->tune.hot_threads = value; break;
         default: return CSR5B200_INVALID_ARGUMENT;
     }
     return CSR5B200_SUCCESS;
@@ -231,6 +309,11 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
     CUF(launch_transpose(pl, true, h->stream));
     CUF(cudaStreamSynchronize(h->stream));
     cudaFree(scan_scratch);
+    scan_scratch = nullptr;
+    {
+        const int err = build_hot_table(h);
+        if (err) { release_csr5_arrays(h); return err; }
+    }
 #undef CUF
     h->format = CSR5B200_FORMAT_CSR5;
     return CSR5B200_SUCCESS;
@@ -242,6 +325,9 @@ int csr5b200_as_csr(csr5b200_handle_t h)
     if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_SUCCESS;
     if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
     if (h->pl.p > 0) {
+        if (h->pl.hot_k > 0)
+            CU(h, launch_hot_restore(h->pl.col, (long long)(h->pl.p - 1) * OMEGA * h->pl.sigma, h->pl.hot_col,
+                                     h->tune.num_sms, h->stream));
         CU(h, launch_transpose(h->pl, false, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
     }
@@ -255,7 +341,7 @@ static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void
     if (!h) return CSR5B200_INVALID_ARGUMENT;
     if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_UNSUPPORTED_CSR_SPMV;
     if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
-    if ((n_dst == 0 && !y) || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
+    if ((n_dst == 0 && !y && h->pl.m > 0) || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
     if (n_dst < 0 || n_dst > CSR5B200_MAX_SCATTER || (n_dst > 0 && !y_dst)) return CSR5B200_INVALID_ARGUMENT;
     for (int k = 0; k < n_dst; k++)
         if (!y_dst[k]) return CSR5B200_INVALID_ARGUMENT;
@@ -301,6 +387,17 @@ int csr5b200_destroy(csr5b200_handle_t h)
     for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
     h->ev.clear();
     h->ev_used = 0;
+    for (int b = 0; b < 2; b++) {
+        cudaFree(h->xb[b]); cudaFree(h->yb[b]);
+        h->xb[b] = h->yb[b] = nullptr;
+        if (h->e_in[b]) cudaEventDestroy(h->e_in[b]);
+        if (h->e_comp[b]) cudaEventDestroy(h->e_comp[b]);
+        if (h->e_out[b]) cudaEventDestroy(h->e_out[b]);
+        h->e_in[b] = h->e_comp[b] = h->e_out[b] = nullptr;
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    h->s_in = h->s_out = nullptr;
     return err;
 }
 
@@ -338,6 +435,8 @@ int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out)
     out->calibrator = pl.calibrator;
     out->last_cuda_error = h->last_cuda_error;
     out->launches_per_spmv = h->launches_per_spmv;
+    out->hot_columns = pl.hot_k;
+    out->hot_coverage = pl.hot_coverage;
     return CSR5B200_SUCCESS;
 }
 
@@ -390,6 +489,62 @@ int csr5b200_spmv_host(csr5b200_handle_t h, double alpha, const void *x_host, vo
     if (err) return err;
     CU(h, cudaMemcpyAsync(y_host, h->y_stage, (size_t)h->pl.m * vb, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_spmv_host_batch(csr5b200_handle_t h, double alpha, int count, const void *const *x_hosts,
+                             void *const *y_hosts)
+{
+    if (!h || count < 0 || (count > 0 && (!x_hosts || !y_hosts))) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNSUPPORTED_CSR_SPMV;
+    if (count == 0) return CSR5B200_SUCCESS;
+    const size_t vb = (size_t)h->pl.value_bytes;
+    const size_t xbytes = (size_t)h->pl.n * vb, ybytes = (size_t)h->pl.m * vb;
+    if (!h->s_in) {
+        CU(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        CU(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CU(h, cudaMalloc(&h->xb[b], xbytes ? xbytes : 1));
+            CU(h, cudaMalloc(&h->yb[b], ybytes ? ybytes : 1));
+            CU(h, cudaEventCreateWithFlags(&h->e_in[b], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->e_comp[b], cudaEventDisableTiming));
+            CU(h, cudaEventCreateWithFlags(&h->e_out[b], cudaEventDisableTiming));
+        }
+    }
+    // work already queued on the handle's stream (e.g. a previous spmv) precedes the pipeline
+    CU(h, cudaEventRecord(h->e_comp[0], h->stream));
+    CU(h, cudaStreamWaitEvent(h->s_in, h->e_comp[0], 0));
+    const void *saved_x = h->pl.x;
+    int err = CSR5B200_SUCCESS;
+    cudaError_t ce = cudaSuccess;
+    auto ok = [&](cudaError_t e) { ce = e; return e == cudaSuccess; };
+    for (int k = 0; k < count && !err && ce == cudaSuccess; k++) {
+        const int b = k & 1;
+        if (!x_hosts[k] || !y_hosts[k]) { err = CSR5B200_INVALID_ARGUMENT; break; }
+        // upload x_k once the SpMV that last read this x buffer (k - 2) is done
+        if (k >= 2 && !ok(cudaStreamWaitEvent(h->s_in, h->e_comp[b], 0))) break;
+        if (!ok(cudaMemcpyAsync(h->xb[b], x_hosts[k], xbytes, cudaMemcpyHostToDevice, h->s_in))) break;
+        if (!ok(cudaEventRecord(h->e_in[b], h->s_in))) break;
+        // SpMV k after its upload and after the download that last read this y buffer (k - 2)
+        if (!ok(cudaStreamWaitEvent(h->stream, h->e_in[b], 0))) break;
+        if (k >= 2 && !ok(cudaStreamWaitEvent(h->stream, h->e_out[b], 0))) break;
+        h->pl.x = h->xb[b];
+        err = csr5b200_spmv(h, alpha, h->yb[b]);
+        if (err) break;
+        if (!ok(cudaEventRecord(h->e_comp[b], h->stream))) break;
+        // download y_k
+        if (!ok(cudaStreamWaitEvent(h->s_out, h->e_comp[b], 0))) break;
+        if (!ok(cudaMemcpyAsync(y_hosts[k], h->yb[b], ybytes, cudaMemcpyDeviceToHost, h->s_out))) break;
+        if (!ok(cudaEventRecord(h->e_out[b], h->s_out))) break;
+    }
+    h->pl.x = saved_x;
+    cudaError_t e1 = cudaStreamSynchronize(h->s_in), e2 = cudaStreamSynchronize(h->stream),
+                e3 = cudaStreamSynchronize(h->s_out);
+    if (err) return err;
+    if (ce != cudaSuccess) return cuda_fail(h, ce);
+    if (e1 != cudaSuccess) return cuda_fail(h, e1);
+    if (e2 != cudaSuccess) return cuda_fail(h, e2);
+    if (e3 != cudaSuccess) return cuda_fail(h, e3);
     return CSR5B200_SUCCESS;
 }
 

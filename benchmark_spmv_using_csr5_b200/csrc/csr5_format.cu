@@ -295,6 +295,62 @@ transpose_kernel(int *__restrict__ col, VT *__restrict__ val, const uint32_t *__
     }
 }
 
+// ---- hot-column table -------------------------------------------------------------------------------
+// cnt[c] = number of references to column c among the first `limit` non-zeros (the CSR5 tiles).
+__global__ void __launch_bounds__(256) hot_count_kernel(const int *__restrict__ col, long long limit, int *cnt)
+{
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < limit; k += (long long)gridDim.x * blockDim.x)
+        atomicAdd(cnt + col[k], 1);
+}
+
+// out2[0] = #columns with cnt >= threshold, out2[1] = references they receive
+__global__ void __launch_bounds__(256)
+hot_count_ge_kernel(const int *__restrict__ cnt, int n, int threshold, unsigned long long *out2)
+{
+    unsigned long long cols = 0, refs = 0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int v = cnt[c];
+        if (v >= threshold) { cols++; refs += (unsigned long long)v; }
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        cols += __shfl_xor_sync(FULL, cols, w);
+        refs += __shfl_xor_sync(FULL, refs, w);
+    }
+    if ((threadIdx.x & 31) == 0 && cols) { atomicAdd(out2, cols); atomicAdd(out2 + 1, refs); }
+}
+
+__global__ void __launch_bounds__(256) hot_flags_kernel(const int *__restrict__ cnt, int n, int threshold, int *slot)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= n) slot[c] = (c < n && cnt[c] >= threshold) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+hot_fill_kernel(const int *__restrict__ cnt, int n, int threshold, const int *__restrict__ slot, int *__restrict__ hot_col)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n && cnt[c] >= threshold) hot_col[slot[c]] = c;
+}
+
+// A hot column index is replaced by (bit 31 | slot); asCSR() undoes it from hot_col[].
+__global__ void __launch_bounds__(256)
+hot_rewrite_kernel(int *col, long long limit, const int *__restrict__ cnt, int threshold, const int *__restrict__ slot)
+{
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < limit; k += (long long)gridDim.x * blockDim.x) {
+        const int c = col[k];
+        if (__ldg(cnt + c) >= threshold) col[k] = (int)(MSB | (uint32_t)__ldg(slot + c));
+    }
+}
+
+__global__ void __launch_bounds__(256) hot_restore_kernel(int *col, long long limit, const int *__restrict__ hot_col)
+{
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < limit; k += (long long)gridDim.x * blockDim.x) {
+        const int c = col[k];
+        if (c < 0) col[k] = __ldg(hot_col + (c & (int)ROW_MASK));
+    }
+}
+
 __global__ void warmup_kernel(int *out)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0 && out) *out = 0;
@@ -328,15 +384,55 @@ size_t scan_scratch_bytes(int p)
     return (size_t)nb * sizeof(int);
 }
 
-cudaError_t launch_scan_offsets(const Plan &pl, void *scratch, size_t scratch_bytes, cudaStream_t stream)
+cudaError_t launch_exclusive_scan(int *data, int n, void *scratch, size_t scratch_bytes, cudaStream_t stream)
 {
-    const int n = pl.p + 1;
     const int nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
     if (scratch_bytes < (size_t)nb * sizeof(int)) return cudaErrorInvalidValue;
     int *block_sums = static_cast<int *>(scratch);
-    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(pl.desc_off_ptr, n, block_sums);
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(data, n, block_sums);
     scan_block_sums_kernel<<<1, SCAN_THREADS, 0, stream>>>(block_sums, nb);
-    scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(pl.desc_off_ptr, n, block_sums);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(data, n, block_sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_offsets(const Plan &pl, void *scratch, size_t scratch_bytes, cudaStream_t stream)
+{
+    return launch_exclusive_scan(pl.desc_off_ptr, pl.p + 1, scratch, scratch_bytes, stream);
+}
+
+// ---- hot-column table (no reference counterpart) ---------------------------------
+cudaError_t launch_hot_count(const int *col, long long limit, int *cnt, int num_sms, cudaStream_t stream)
+{
+    hot_count_kernel<<<num_sms * 16, 256, 0, stream>>>(col, limit, cnt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hot_count_ge(const int *cnt, int n, int threshold, unsigned long long *out2, int num_sms,
+                                cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    hot_count_ge_kernel<<<num_sms * 4, 256, 0, stream>>>(cnt, n, threshold, out2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hot_flags(const int *cnt, int n, int threshold, int *slot, cudaStream_t stream)
+{
+    hot_flags_kernel<<<(n + 1 + 255) / 256, 256, 0, stream>>>(cnt, n, threshold, slot);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hot_assign(const int *cnt, int n, int threshold, const int *slot, int *hot_col, int *col,
+                              long long limit, int num_sms, cudaStream_t stream)
+{
+    hot_fill_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cnt, n, threshold, slot, hot_col);
+    hot_rewrite_kernel<<<num_sms * 16, 256, 0, stream>>>(col, limit, cnt, threshold, slot);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hot_restore(int *col, long long limit, const int *hot_col, int num_sms, cudaStream_t stream)
+{
+    hot_restore_kernel<<<num_sms * 16, 256, 0, stream>>>(col, limit, hot_col);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,14 @@ struct Plan {
     int *desc_off = nullptr;        // owned, num_offsets
     void *calibrator = nullptr;     // owned, p values
     int *dev_flags = nullptr;       // owned, small scratch: [0] any dirty tile before the tail
+
+    // Hot-column table (no reference counterpart).  While hot_k > 0 the column indices
+    // of the hot_k most referenced columns are stored in the CSR5 tiles as (bit 31 | slot); asCSR()
+    // restores them.  The SpMV stages x[hot_col[*]] in shared memory.
+    int hot_k = 0;
+    int *hot_col = nullptr;         // owned, hot_k entries: slot -> column
+    void *hot_x = nullptr;          // owned, hot_k values (16-byte padded): x[hot_col[slot]], refreshed per SpMV
+    double hot_coverage = 0.0;      // fraction of the tiles' column references that hit the table
 };
 
 struct SpmvTuning {
@@ -48,6 +56,8 @@ struct SpmvTuning {
     int num_sms = 148;
     int direct_wpb = 0;    // tuning: warps per CTA of the direct kernel (0 = default 4)
     int direct_nch = 0;    // tuning: register chunks per tile (0 = default rule)
+    int hot_columns = 0;   // 0 off (default), -1 auto (kept if it serves >= 25 % of the references), > 0 capacity
+    int hot_threads = 0;   // tuning: threads per CTA of the hot-column kernel (0 = default)
     cudaEvent_t ev_begin = nullptr;  // optional: recorded right before / after the main SpMV kernel
     cudaEvent_t ev_end = nullptr;
 };
@@ -58,7 +68,16 @@ struct SpmvTuning {
 cudaError_t launch_tile_ptr(const Plan &pl, cudaStream_t stream);
 cudaError_t launch_tile_desc(const Plan &pl, cudaStream_t stream);
 cudaError_t launch_scan_offsets(const Plan &pl, void *scratch, size_t scratch_bytes, cudaStream_t stream);
-size_t scan_scratch_bytes(int p);
+size_t scan_scratch_bytes(int p);   // for an exclusive scan of p + 1 ints
+cudaError_t launch_exclusive_scan(int *data, int n, void *scratch, size_t scratch_bytes, cudaStream_t stream);
+// hot-column table construction / removal
+cudaError_t launch_hot_count(const int *col, long long limit, int *cnt, int num_sms, cudaStream_t stream);
+cudaError_t launch_hot_count_ge(const int *cnt, int n, int threshold, unsigned long long *out2, int num_sms,
+                                cudaStream_t stream);
+cudaError_t launch_hot_flags(const int *cnt, int n, int threshold, int *slot, cudaStream_t stream);
+cudaError_t launch_hot_assign(const int *cnt, int n, int threshold, const int *slot, int *hot_col, int *col,
+                              long long limit, int num_sms, cudaStream_t stream);
+cudaError_t launch_hot_restore(int *col, long long limit, const int *hot_col, int num_sms, cudaStream_t stream);
 cudaError_t launch_desc_offset(const Plan &pl, cudaStream_t stream);
 // in-place omega x sigma tile transpose of col and val; r2c = CSR -> CSR5.
 cudaError_t launch_transpose(const Plan &pl, bool r2c, cudaStream_t stream);

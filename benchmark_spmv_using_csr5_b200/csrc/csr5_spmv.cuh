@@ -119,6 +119,25 @@ struct GlobalTile {  // direct-load kernel: streaming loads, evict-first
     __device__ __forceinline__ VT v(int i, int lane) const { return __ldcs(val + i * OMEGA + lane); }
     __device__ __forceinline__ int c(int i, int lane) const { return __ldcs(col + i * OMEGA + lane); }
     __device__ __forceinline__ uint32_t d(int k, int lane) const { return __ldg(desc + k * OMEGA + lane); }
+    __device__ __forceinline__ VT xv(const VT *__restrict__ x, int c) const { return __ldg(x + c); }
+};
+
+// Direct loads as GlobalTile, but a column index with bit 31 set names a slot of the hot-column
+// table staged in shared memory (Plan::hot_k) instead of an element of x.
+template <typename VT>
+struct HotTile {
+    static constexpr bool kStageInRegisters = true;
+    const VT *val;
+    const int *col;
+    const uint32_t *desc;
+    const VT *xs;  // shared memory
+    __device__ __forceinline__ VT v(int i, int lane) const { return __ldcs(val + i * OMEGA + lane); }
+    __device__ __forceinline__ int c(int i, int lane) const { return __ldcs(col + i * OMEGA + lane); }
+    __device__ __forceinline__ uint32_t d(int k, int lane) const { return __ldg(desc + k * OMEGA + lane); }
+    __device__ __forceinline__ VT xv(const VT *__restrict__ x, int c) const
+    {
+        return c < 0 ? xs[c & 0x7fffffff] : __ldg(x + c);
+    }
 };
 
 template <typename VT>
@@ -130,12 +149,17 @@ struct SharedTile {  // TMA-staged kernel: conflict-free LDS (consecutive lanes,
     __device__ __forceinline__ VT v(int i, int lane) const { return val[i * OMEGA + lane]; }
     __device__ __forceinline__ int c(int i, int lane) const { return col[i * OMEGA + lane]; }
     __device__ __forceinline__ uint32_t d(int k, int lane) const { return desc[k * OMEGA + lane]; }
+    __device__ __forceinline__ VT xv(const VT *__restrict__ x, int c) const { return __ldg(x + c); }
 };
 
 // ---- one CSR5 tile (t < p - 1) ------------------------------------------------------------------
-// number of register chunks a tile's sigma elements are consumed in (0 = default rule)
-template <int SIGMA, int NCH> struct ChunkOf {
-    static constexpr int N = NCH > 0 ? NCH : (SIGMA <= 16 ? 1 : 2);
+// Number of register chunks a tile's sigma elements are consumed in (NCH = 0: default rule).  Measured on
+// B200 (profiles/r01_sweep_wpb_nch.txt): FP64 is fastest with <= 8 elements (96 B of stream) in flight
+// per lane -- sigma 16 in two chunks streams C2 at 1.00 of the measured copy bandwidth vs 0.97 in one;
+// FP32 is fastest with the whole lane (sigma <= 26) in one chunk.
+template <typename VT, int SIGMA, int NCH> struct ChunkOf {
+    static constexpr int AUTO = sizeof(VT) == 8 ? (SIGMA + 7) / 8 : (SIGMA <= 26 ? 1 : 2);
+    static constexpr int N = NCH > 0 ? NCH : AUTO;
     static constexpr int CH = (SIGMA + N - 1) / N;
 };
 
@@ -145,7 +169,7 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
 {
     // Elements are consumed in register chunks so that all streaming loads and x gathers of a chunk
     // are in flight together without spilling at sigma = 32.
-    constexpr int CH = ChunkOf<SIGMA, NCH>::CH;
+    constexpr int CH = ChunkOf<VT, SIGMA, NCH>::CH;
     const int row_start = (int)(raw_start & ROW_MASK);
     const int row_stop = (int)(raw_stop & ROW_MASK);
     const VT *__restrict__ x = a.x;
@@ -164,7 +188,7 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
             }
 #pragma unroll
             for (int k = 0; k < CH; k++)
-                if (c0 + k < SIGMA) xv[k] = __ldg(x + (Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane)));
+                if (c0 + k < SIGMA) xv[k] = tile.xv(x, Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane));
 #pragma unroll
             for (int k = 0; k < CH; k++)
                 if (c0 + k < SIGMA)
@@ -203,7 +227,7 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
         }
 #pragma unroll
         for (int k = 0; k < CH; k++)
-            if (c0 + k < SIGMA) xv[k] = __ldg(x + (Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane)));
+            if (c0 + k < SIGMA) xv[k] = tile.xv(x, Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane));
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const int i = c0 + k;
@@ -331,6 +355,13 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy()
     return pol;
 }
 
+__device__ __forceinline__ uint64_t l2_evict_last_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
 constexpr int TMA_MAX_WARPS = 16;
 
 template <typename VT, int SIGMA>
@@ -417,6 +448,60 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
     }
 }
 
+// ---- hot-column kernel (power-law matrices) ------------------------------------------------------
+// The x gathers of a scale-free matrix are uncoalesced 32-byte sectors, and an SM's L1TEX pipeline
+// retires about one such sector per clock -- that, not HBM, bounds the direct kernel on R-MAT
+// (profiles/r01_c3_*).  Here the most referenced columns (Plan::hot_k of them, chosen at asCSR5() time)
+// are served from shared memory instead: a tiny pre-kernel gathers x[hot_col[*]] into a dense array,
+// every persistent CTA pulls that array into shared memory with 1-D bulk TMA copies completing on an
+// mbarrier, and the tile loop reads tagged columns with LDS (a handful of bank-conflict wavefronts per
+// warp instead of 32 L1TEX wavefronts).
+template <typename VT>
+__global__ void __launch_bounds__(256)
+hot_gather_kernel(const VT *__restrict__ x, const int *__restrict__ hot_col, VT *__restrict__ hot_x, int hot_k)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < hot_k) hot_x[j] = __ldg(x + __ldg(hot_col + j));
+}
+
+constexpr int HOT_MAX_THREADS = 1024;
+
+template <typename VT, int SIGMA, bool MULTI, int NCH = 0>
+__global__ void __launch_bounds__(HOT_MAX_THREADS, 1)
+spmv_hot_kernel(const SpmvArgs<VT> a, const VT *__restrict__ hot_x, const uint32_t hot_bytes)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    VT *xs = reinterpret_cast<VT *>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + hot_bytes);
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(smem_u32(bar), hot_bytes);
+        const uint64_t policy = l2_evict_last_policy();  // 148 CTAs re-read the same few KB
+        constexpr uint32_t PIECE = 32768;
+        for (uint32_t off = 0; off < hot_bytes; off += PIECE) {
+            const uint32_t n = hot_bytes - off < PIECE ? hot_bytes - off : PIECE;
+            tma_load_1d(smem_u32(smem + off), reinterpret_cast<const unsigned char *>(hot_x) + off, n, smem_u32(bar),
+                        policy);
+        }
+    }
+    __syncthreads();
+    mbar_wait(smem_u32(bar), 0);
+
+    const long long GW = (long long)gridDim.x * wpb;
+    const long long gw = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
+    for (long long tw = gw; tw < a.tail_warps; tw += GW) process_tail_rows<VT, MULTI>(a, (int)tw, lane);
+    const long long ntiles = a.p - 1;
+    for (long long tl = gw; tl < ntiles; tl += GW) {
+        const int t = (int)tl;
+        const size_t base = (size_t)t * (OMEGA * SIGMA);
+        HotTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet, xs};
+        process_tile<VT, SIGMA, MULTI, HotTile<VT>, NCH>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
+    }
+}
+
 // ---- carries: y[row of tile t] += calibrator[t] for the tiles whose first row began earlier -----
 template <typename VT, bool MULTI>
 __global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a)
@@ -438,9 +523,32 @@ __global__ void __launch_bounds__(256) zero_rows_kernel(const SpmvArgs<VT> a)
 // ---- host-side dispatch ----------------------------------------------------------------------------
 template <typename VT, int SIGMA>
 cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_ok, cudaStream_t stream,
-                         int *used)
+                         int *used, int hot_k, const VT *hot_x)
 {
     const long long ntiles = a.p - 1;
+    if (hot_k > 0 && ntiles > 0) {
+        // column indices are tagged: only the hot-column kernel can read them
+        const uint32_t hot_bytes = (uint32_t)(((size_t)hot_k * sizeof(VT) + 15) / 16 * 16);
+        const size_t smem = hot_bytes + 16;
+        int threads = tn.hot_threads > 0 ? tn.hot_threads : 768;
+        if (threads > HOT_MAX_THREADS) threads = HOT_MAX_THREADS;
+        threads = (threads + 31) / 32 * 32;
+        cudaError_t e;
+        auto run = [&](auto kern) -> cudaError_t {
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess)
+                return e;
+            kern<<<tn.num_sms, threads, smem, stream>>>(a, hot_x, hot_bytes);
+            return cudaGetLastError();
+        };
+        *used = 3;
+        if constexpr (SIGMA == 15 || SIGMA == 16) {
+            if (a.n_dst == 0 && tn.direct_nch == 1) return run(spmv_hot_kernel<VT, SIGMA, false, 1>);
+            if (a.n_dst == 0 && tn.direct_nch == 2) return run(spmv_hot_kernel<VT, SIGMA, false, 2>);
+            if (a.n_dst == 0 && tn.direct_nch == 3) return run(spmv_hot_kernel<VT, SIGMA, false, 3>);
+            if (a.n_dst == 0 && tn.direct_nch == 4) return run(spmv_hot_kernel<VT, SIGMA, false, 4>);
+        }
+        return a.n_dst > 0 ? run(spmv_hot_kernel<VT, SIGMA, true>) : run(spmv_hot_kernel<VT, SIGMA, false>);
+    }
     int kernel = tn.kernel;
     // auto = direct-load: on B200 it streams C2 at 98 % of the measured HBM copy bandwidth vs 87 % for
     // the TMA-staged ring (profiles/r01_*; the ring's few, fat warps expose the x-gather latency).
@@ -457,14 +565,16 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
         if constexpr (SIGMA == 15 || SIGMA == 16 || SIGMA == 26) {
             if (a.n_dst == 0 && (tn.direct_wpb > 0 || tn.direct_nch > 0)) {
                 const int wpb = tn.direct_wpb > 0 ? tn.direct_wpb : 4;
-                const int nch = tn.direct_nch > 0 ? tn.direct_nch : ChunkOf<SIGMA, 0>::N;
+                const int nch = tn.direct_nch > 0 ? tn.direct_nch : ChunkOf<VT, SIGMA, 0>::N;
 #define CSR5_VARIANT(W, N)                                                                                   \
     if (wpb == W && nch == N) {                                                                              \
         spmv_direct_kernel<VT, SIGMA, W, false, N><<<(unsigned)((units + W - 1) / W), W * 32, 0, stream>>>(a); \
         return cudaGetLastError();                                                                           \
     }
-                CSR5_VARIANT(2, 1) CSR5_VARIANT(2, 2) CSR5_VARIANT(4, 1) CSR5_VARIANT(4, 2) CSR5_VARIANT(8, 1)
-                CSR5_VARIANT(8, 2) CSR5_VARIANT(16, 1) CSR5_VARIANT(16, 2) CSR5_VARIANT(4, 3) CSR5_VARIANT(8, 3)
+                CSR5_VARIANT(2, 1) CSR5_VARIANT(2, 2) CSR5_VARIANT(2, 3) CSR5_VARIANT(2, 4)
+                CSR5_VARIANT(4, 1) CSR5_VARIANT(4, 2) CSR5_VARIANT(4, 3) CSR5_VARIANT(4, 4)
+                CSR5_VARIANT(8, 1) CSR5_VARIANT(8, 2) CSR5_VARIANT(8, 3) CSR5_VARIANT(8, 4)
+                CSR5_VARIANT(16, 2) CSR5_VARIANT(16, 4)
 #undef CSR5_VARIANT
                 return cudaErrorInvalidValue;
             }
@@ -557,9 +667,15 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
                         (reinterpret_cast<uintptr_t>(a.col) % 16 == 0) &&
                         (reinterpret_cast<uintptr_t>(a.desc) % 16 == 0);
 
+    if (pl.hot_k > 0 && pl.p > 1) {
+        hot_gather_kernel<VT><<<(pl.hot_k + 255) / 256, 256, 0, stream>>>(a.x, pl.hot_col, static_cast<VT *>(pl.hot_x),
+                                                                        pl.hot_k);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++*launches;
+    }
     if (tn.ev_begin && (e = cudaEventRecord(tn.ev_begin, stream)) != cudaSuccess) return e;
     switch (pl.sigma) {
-#define CSR5_CASE(S) case S: e = launch_sigma<VT, S>(a, tn, tma_ok, stream, used); break;
+#define CSR5_CASE(S) case S: e = launch_sigma<VT, S>(a, tn, tma_ok, stream, used, pl.hot_k, static_cast<const VT *>(pl.hot_x)); break;
         CSR5_CASE(4) CSR5_CASE(5) CSR5_CASE(6) CSR5_CASE(7) CSR5_CASE(8) CSR5_CASE(9) CSR5_CASE(10)
         CSR5_CASE(11) CSR5_CASE(12) CSR5_CASE(13) CSR5_CASE(14) CSR5_CASE(15) CSR5_CASE(16)
         CSR5_CASE(17) CSR5_CASE(18) CSR5_CASE(19) CSR5_CASE(20) CSR5_CASE(21) CSR5_CASE(22)

@@ -45,7 +45,9 @@ OPT_CTAS_PER_SM = 5
 OPT_KERNEL_TIMING = 6
 OPT_DIRECT_WPB = 7
 OPT_DIRECT_NCH = 8
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA = 0, 1, 2
+OPT_HOT_COLUMNS = 9
+OPT_HOT_THREADS = 10
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_HOT = 0, 1, 2, 3
 
 
 def _ptr(t):
@@ -139,6 +141,17 @@ class anonymouslibHandle:
         self._bind_stream()
         return self._lib.csr5b200_spmv_host(self._h, float(alpha), self._host_ptr(x_host, self.n),
                                             self._host_ptr(y_host, self.m))
+
+    def spmv_host_batch(self, alpha: float, x_hosts, y_hosts) -> int:
+        """Pipelined y_k = alpha * A * x_k for lists of host vectors (pinned for full overlap):
+        upload of x_{k+1}, SpMV of x_k and download of y_{k-1} run concurrently."""
+        if len(x_hosts) != len(y_hosts):
+            raise ValueError("x_hosts and y_hosts must have the same length")
+        self._bind_stream()
+        k = len(x_hosts)
+        xs = (C.c_void_p * k)(*[self._host_ptr(a, self.n) for a in x_hosts])
+        ys = (C.c_void_p * k)(*[self._host_ptr(a, self.m) for a in y_hosts])
+        return self._lib.csr5b200_spmv_host_batch(self._h, float(alpha), k, xs, ys)
 
     def info(self) -> _lib.Csr5Info:
         out = _lib.Csr5Info()

@@ -114,6 +114,10 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
                                          (see csr5b200_get_kernel_times); 0 = off (default) */
 #define CSR5B200_OPT_DIRECT_WPB    7  /* tuning: warps per CTA of the direct kernel (2/4/8/16; 0 = default) */
 #define CSR5B200_OPT_DIRECT_NCH    8  /* tuning: register chunks per tile (1/2/3; 0 = default rule) */
+#define CSR5B200_OPT_HOT_COLUMNS    9  /* hot-column table, decided at as_csr5(): 0 off (default), -1 auto (kept when it
+                                         serves >= 25 % of the x references), K > 0 = table capacity in entries.
+                                         While it is on, the tagged occurrences in `col` read (bit 31 | slot). */
+#define CSR5B200_OPT_HOT_THREADS   10 /* tuning: threads per CTA of the hot-column kernel (0 = default 768) */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays
@@ -130,7 +134,7 @@ typedef struct csr5b200_info {
     int num_offsets;       /* _num_offsets */
     int tail_partition_start; /* _tail_partition_start */
     int needs_zero_fill;   /* 1 if some row before the tail is empty (y is memset inside spmv) */
-    int kernel_in_use;     /* 1 direct-load, 2 TMA-staged */
+    int kernel_in_use;     /* 1 direct-load, 2 TMA-staged, 3 hot-column (direct-load + x table in shared memory) */
     const uint32_t *partition_pointer;           /* (p + 1) */
     const uint32_t *partition_descriptor;        /* p * 32 * num_packet */
     const int32_t  *partition_descriptor_offset_pointer; /* (p + 1) */
@@ -138,6 +142,8 @@ typedef struct csr5b200_info {
     const void     *calibrator;                  /* p values */
     int last_cuda_error;   /* cudaError_t of the last failing CUDA call, 0 if none */
     int launches_per_spmv; /* kernels (+ memset nodes) one spmv() enqueues */
+    int hot_columns;       /* entries of the hot-column table in use (0 = none) */
+    double hot_coverage;   /* fraction of the tiles' x references served by the table */
 } csr5b200_info;
 CSR5B200_API int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out);
 
@@ -158,6 +164,13 @@ CSR5B200_API int csr5b200_copy_meta_to_host(csr5b200_handle_t h, uint32_t *parti
  *   spmv_host: H2D copy of x (n values), spmv, D2H copy of y (m values), synchronous.
  *   x_host / y_host may be pageable or pinned; the handle owns the device staging buffers. */
 CSR5B200_API int csr5b200_spmv_host(csr5b200_handle_t h, double alpha, const void *x_host, void *y_host);
+
+/* `count` independent SpMVs y_k = alpha * A * x_k on host vectors, software-pipelined: the upload of
+ * x_{k+1}, the SpMV of x_k and the download of y_{k-1} run concurrently (two device buffers per
+ * direction, separate copy streams, PCIe is full duplex).  x_hosts[k] / y_hosts[k] should be pinned for
+ * the copies to be asynchronous.  Synchronous: returns when every y_k is in host memory. */
+CSR5B200_API int csr5b200_spmv_host_batch(csr5b200_handle_t h, double alpha, int count, const void *const *x_hosts,
+                                          void *const *y_hosts);
 
 /* One-shot equivalent of call_anonymouslib() without the benchmark loop: uploads the CSR arrays
  * and x, converts, runs ONE spmv, downloads y, restores and frees everything. */

@@ -29,6 +29,12 @@ def _upload(torch, A, val, x):
             torch.from_numpy(val).to(dev), torch.from_numpy(x).to(dev))
 
 
+# kernel ids: 1 direct-load, 2 TMA-staged (both with the hot-column table off), 3 hot-column kernel with
+# the automatic table, 4 hot-column kernel with a tiny forced table (tagged and untagged columns mixed)
+KERNELS = [1, 2, 3, 4]
+KERNEL_IDS = ["direct", "tma", "hot_auto", "hot_k48"]
+
+
 def _handle(torch, A, val, x, sigma, kernel=0):
     from benchmark_spmv_using_csr5_b200 import handle as H
     tdt = torch.float64 if val.dtype == np.float64 else torch.float32
@@ -37,7 +43,8 @@ def _handle(torch, A, val, x, sigma, kernel=0):
     assert h.inputCSR(A.nnz, rp, ci, v) == 0
     assert h.setX(xd) == 0
     h.setSigma(sigma)
-    assert h.set_option(H.OPT_KERNEL, kernel) == 0
+    assert h.set_option(H.OPT_KERNEL, kernel if kernel in (0, 1, 2) else 0) == 0
+    assert h.set_option(H.OPT_HOT_COLUMNS, {0: -1, 1: 0, 2: 0, 3: -1, 4: 48}[kernel]) == 0
     assert h.warmup() == 0
     assert h.asCSR5() == 0
     return h, (rp, ci, v, xd)
@@ -50,7 +57,7 @@ def _spmv(torch, h, m, dtype, alpha=1.0, fill=float("nan")):
     return y.cpu().numpy()
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "tma"])
+@pytest.mark.parametrize("kernel", KERNELS, ids=KERNEL_IDS)
 @pytest.mark.parametrize("name,A,sigma", CASES, ids=[c[0] for c in CASES])
 def test_y_int_bit_exact_and_real(torch_cuda, oracle, name, A, sigma, kernel):
     torch = torch_cuda
@@ -76,7 +83,7 @@ def test_metadata_word_for_word(torch_cuda, oracle, name, A, sigma):
     if A.nnz == 0:
         pytest.skip("empty")
     val, x = M.values(A.nnz, A.n, "int")
-    h, _keep = _handle(torch, A, val, x, sigma)
+    h, _keep = _handle(torch, A, val, x, sigma, kernel=1)   # hot-column table off: col is the reference's
     got = h.meta_to_host()
     s = sigma if sigma > 0 else oracle.auto_sigma(A.m, A.nnz)
     want = oracle.csr5_meta(A.m, A.nnz, s, A.row_ptr)
@@ -101,7 +108,7 @@ def test_metadata_word_for_word(torch_cuda, oracle, name, A, sigma):
     h.free()
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "tma"])
+@pytest.mark.parametrize("kernel", KERNELS, ids=KERNEL_IDS)
 def test_all_sigmas(torch_cuda, oracle, kernel):
     torch = torch_cuda
     A = sigma_sweep_case()
@@ -114,7 +121,7 @@ def test_all_sigmas(torch_cuda, oracle, kernel):
         h.free()
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["direct", "tma"])
+@pytest.mark.parametrize("kernel", KERNELS, ids=KERNEL_IDS)
 def test_fp32(torch_cuda, oracle, kernel):
     torch = torch_cuda
     for name, A, sigma in CASES:
@@ -242,7 +249,7 @@ def _segment_sums_exact(torch, rp, ci, v, x):
     return cs[rp[1:].long()] - cs[rp[:-1].long()]
 
 
-def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2)):
+def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2, 3)):
     from benchmark_spmv_using_csr5_b200 import handle as H
     m, n, nnz = rp.numel() - 1, x.numel(), ci.numel()
     y_ref = _segment_sums_exact(torch, rp, ci, v, x).to(dtype)
@@ -252,7 +259,8 @@ def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2)):
         assert h.inputCSR(nnz, rp, ci, v) == 0
         h.setX(x)
         h.setSigma(-1)
-        h.set_option(H.OPT_KERNEL, kernel)
+        h.set_option(H.OPT_KERNEL, kernel if kernel < 3 else 0)
+        h.set_option(H.OPT_HOT_COLUMNS, -1 if kernel == 3 else 0)
         assert h.asCSR5() == 0
         y = torch.full((m,), float("nan"), device="cuda", dtype=dtype)
         assert h.spmv(1.0, y) == 0
@@ -285,3 +293,42 @@ def test_full_size_c3_rmat22(torch_cuda):
     n = rp.numel() - 1
     v, x = M.device_values(ci.numel(), n, "int", torch.float64, "cuda")
     _full_size_check(torch, rp, ci, v, x, torch.float64)
+
+
+def test_hot_column_table(torch_cuda, oracle):
+    """The hot-column table (no reference counterpart): chosen at asCSR5(), tags col in place, asCSR()
+    restores col bit for bit; auto mode drops it when it would serve < 25 % of the references."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    A = M.rmat(14)
+    val, x = M.values(A.nnz, A.n, "int")
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    for cap in (-1, 16, 1000, 100000):
+        h, keep = _handle(torch, A, val, x, -1, kernel=1)
+        h.asCSR()
+        h.set_option(H.OPT_HOT_COLUMNS, cap)
+        assert h.asCSR5() == 0
+        info = h.info()
+        assert info.hot_columns > 0 and 0.0 < info.hot_coverage <= 1.0
+        if cap > 0:
+            assert info.hot_columns <= cap
+        tagged = (keep[1].cpu().numpy() < 0)
+        live = (info.p - 1) * 32 * info.sigma
+        assert tagged[:live].any() and not tagged[live:].any()          # the tail tile is never tagged
+        assert abs(tagged[:live].mean() - info.hot_coverage) < 1e-9
+        y = _spmv(torch, h, A.m, torch.float64)
+        assert h.info().kernel_in_use == H.KERNEL_HOT
+        assert np.array_equal(y, y_ref), cap
+        assert h.asCSR() == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(keep[1].cpu().numpy(), A.col) and np.array_equal(keep[2].cpu().numpy(), val)
+        h.free()
+    # banded: every column is referenced equally often and there are more of them than slots -> no table
+    B = M.banded(200_000, 16)
+    val, x = M.values(B.nnz, B.n, "int")
+    h, keep = _handle(torch, B, val, x, -1, kernel=0)
+    assert h.info().hot_columns == 0
+    y = _spmv(torch, h, B.m, torch.float64)
+    assert h.info().kernel_in_use == H.KERNEL_DIRECT
+    assert np.array_equal(y, oracle.csr_spmv(B.m, B.row_ptr, B.col, val, x))
+    h.free()

@@ -34,7 +34,8 @@ def _ours(A, val, x, sigma, kernel=0):
     h = H.anonymouslibHandle(A.m, A.n, tdt)
     assert h.inputCSR(A.nnz, rp, ci, v) == 0 and h.setX(xd) == 0
     h.setSigma(sigma)
-    h.set_option(H.OPT_KERNEL, kernel)
+    h.set_option(H.OPT_KERNEL, kernel if kernel < 3 else 0)
+    h.set_option(H.OPT_HOT_COLUMNS, -1 if kernel == 3 else 0)   # table off: col stays the reference's
     assert h.asCSR5() == 0
     y = torch.zeros(A.m, device="cuda", dtype=tdt)
     assert h.spmv(1.0, y) == 0
@@ -50,7 +51,7 @@ def _ours(A, val, x, sigma, kernel=0):
 def test_against_reference_cuda(refcuda, name, A, sigma, dtype):
     val, x = M.values(A.nnz, A.n, "int", dtype)
     ref = refcuda.ref_cuda_spmv(A.m, A.n, A.row_ptr, A.col, val, x, sigma, 1)
-    for kernel in (1, 2):
+    for kernel in (3, 1, 2):
         y, meta = _ours(A, val, x, sigma, kernel)
         assert np.array_equal(y, ref["y"]), f"{name}: y differs from the reference's CSR5_cuda (kernel {kernel})"
     for k in ("sigma", "bit_y", "bit_ss", "num_packet", "p", "tail_start"):
@@ -73,7 +74,7 @@ def test_against_reference_cuda(refcuda, name, A, sigma, dtype):
     # real-valued inputs
     val, x = M.values(A.nnz, A.n, "real", dtype)
     ref = refcuda.ref_cuda_spmv(A.m, A.n, A.row_ptr, A.col, val, x, sigma, 1)
-    y, _ = _ours(A, val, x, sigma)
+    y, _ = _ours(A, val, x, sigma, 3)
     rtol = 1e-12 if dtype == np.float64 else 2e-5
     assert np.allclose(y, ref["y"], rtol=rtol, atol=0 if dtype == np.float64 else 1e-5), name
 

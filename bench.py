@@ -35,7 +35,9 @@ WORKLOADS = {
     "c2": "banded 10M x 10M, 16 nnz/row, FP64 (BASELINE.json configs[1])",
     "c3": "R-MAT scale 22, edge factor 16, FP64 (BASELINE.json configs[2])",
     "c4": "27-pt Laplacian 320^3, FP32 (BASELINE.json configs[3])",
+    "c5": "R-MAT scale 25, edge factor 16, FP64, row-range sharded by balanced nnz (BASELINE.json configs[4])",
 }
+STRONG = {"c3", "c5"}   # fixed matrix split over the ranks (strong scaling); c2 grows with N (weak)
 
 
 def log(*a):
@@ -129,23 +131,33 @@ def build_workload(name, torch, device, rank, world):
         dtype = torch.float64
         val, _ = M.device_values(ci.numel(), 1, "real", dtype, device, seed=42 + rank)
         _, x = M.device_values(1, n, "real", dtype, device, seed=4242)  # same x on every rank
-        return dict(row_ptr=rp, col=ci, val=val, x=x, m=m_local, n=n, row_begin=rank * m_local, dtype=dtype)
-    if world != 1:
-        raise SystemExit(f"workload {name} is a single-GPU configuration")
-    if name == "c3":
-        rp, ci = M.device_rmat(22, device=device)
+        return dict(row_ptr=rp, col=ci, val=val, x=x, m=m_local, n=n, dtype=dtype,
+                    bounds=np.arange(world + 1, dtype=np.int64) * m_local)
+    if name in ("c3", "c5"):
+        # every rank generates the same seeded matrix and keeps its nnz-balanced row range
+        from benchmark_spmv_using_csr5_b200 import sharded as S
+        rp, ci = M.device_rmat(22 if name == "c3" else 25, device=device)
         n = rp.numel() - 1
         dtype = torch.float64
-    elif name == "c4":
+        val, x = M.device_values(ci.numel(), n, "real", dtype, device, seed=42)
+        bounds = S.row_partition(rp, world)
+        if world > 1:
+            lrp, lci, lval = S.shard_csr(rp, ci, val, int(bounds[rank]), int(bounds[rank + 1]))
+            lrp, lci, lval = lrp.contiguous(), lci.clone(), lval.clone()
+            del rp, ci, val
+            torch.cuda.empty_cache()
+            rp, ci, val = lrp, lci, lval
+        return dict(row_ptr=rp, col=ci, val=val, x=x, m=int(bounds[rank + 1] - bounds[rank]), n=n, dtype=dtype,
+                    bounds=bounds)
+    if world != 1:
+        raise SystemExit(f"workload {name} is a single-GPU configuration")
+    if name == "c4":
         rp, ci, val = M.device_laplacian27(320, device=device, dtype=torch.float32)
         n = rp.numel() - 1
         dtype = torch.float32
         _, x = M.device_values(1, n, "real", dtype, device, seed=42)
-        return dict(row_ptr=rp, col=ci, val=val, x=x, m=n, n=n, row_begin=0, dtype=dtype)
-    else:
-        raise SystemExit(f"unknown workload {name}")
-    val, x = M.device_values(ci.numel(), n, "real", dtype, device, seed=42)
-    return dict(row_ptr=rp, col=ci, val=val, x=x, m=n, n=n, row_begin=0, dtype=dtype)
+        return dict(row_ptr=rp, col=ci, val=val, x=x, m=n, n=n, dtype=dtype, bounds=np.array([0, n], np.int64))
+    raise SystemExit(f"unknown workload {name}")
 
 
 def algorithmic_bytes(m, n, nnz, vb):
@@ -279,7 +291,9 @@ def main():
     vb = 8 if dtype == torch.float64 else 4
 
     from benchmark_spmv_using_csr5_b200 import sharded as S
-    bounds = np.arange(world + 1, dtype=np.int64) * m   # weak scaling: equal row ranges
+    bounds = w["bounds"]            # global row boundaries of the ranks' shards
+    m_total = int(bounds[-1])
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     mode = args.exchange if world > 1 else "local"
     sh = S.ShardedCsr5(bounds, n, w["row_ptr"], w["col"], w["val"], mode="fused" if mode == "fused" else "nccl",
                        sigma=args.sigma)
@@ -384,7 +398,7 @@ def main():
             S.allgather_v(y_full, bounds, rank)
         ms_nccl = time_loop(nccl_step, 3, k2)
         link_gbs = 770.0  # measured peer-copy bandwidth per direction per GPU (B200_PROFILING.md)
-        in_bytes = (world - 1) * m * vb
+        in_bytes = (m_total - m) * vb
         t_link = in_bytes / (link_gbs * 1e6)
         multi = {"exchange": mode, "ms_per_step_spmv_only_no_exchange": ms_local,
                  "ms_per_step_spmv_then_nccl_allgather": ms_nccl, "ms_per_step_fused_peer_stores": ms_step
@@ -420,8 +434,9 @@ def main():
                    "y D2H, software-pipelined (upload k+1 | SpMV k | download k-1); CSR5 matrix resident")
         else:
             x_dev = w["x"]
-            x_slice_dev = x_dev[rank * m:(rank + 1) * m]           # n = world * m: rank g uploads x[g*m:(g+1)*m]
-            x_slice_host = x_host[rank * m:(rank + 1) * m]
+            xs0, xs1 = rank * (n // world), (rank + 1) * (n // world)   # rank g uploads its 1/N slice of x
+            x_slice_dev, x_slice_host = x_dev[xs0:xs1], x_host[xs0:xs1]
+            assert n % world == 0
 
             def e2e_step():   # every rank: upload ITS slice of x over PCIe, replicate x over NVLink (NCCL
                 #               all-gather), sharded SpMV + fused y exchange, download its rows of y
@@ -443,7 +458,7 @@ def main():
         assert torch.allclose(y_host.to(device), y, rtol=1e-12 if vb == 8 else 1e-5, atol=0), \
             "host-buffer path disagrees with the device path"
         e2e = {"value": 2.0 * total_nnz / (e_ms * 1e6), "unit": "GFLOP/s", "h2d_bytes_per_step": n * vb,
-               "d2h_bytes_per_step": m * world * vb, "ms_per_step": e_ms, "steps": e_steps, "api": api,
+               "d2h_bytes_per_step": m_total * vb, "ms_per_step": e_ms, "steps": e_steps, "api": api,
                "ms_per_step_unpipelined_single_call": e2e_sync_ms}
     sampler.stop()
 
@@ -482,12 +497,12 @@ def main():
     out = {
         "metric": "FP64 SpMV GFLOPS" if vb == 8 else "FP32 SpMV GFLOPS",
         "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None,
         "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
         "config": {
-            "workload": WORKLOADS[args.workload] + (f"; rank g owns rows [g*{m}, (g+1)*{m}) of the {n}-row matrix, "
+            "workload": WORKLOADS[args.workload] + (f"; rank g owns rows [bounds[g], bounds[g+1]) of the {m_total}-row matrix, "
                                                     f"x replicated, y concatenated on every rank each step ({mode})" if world > 1 else ""),
-            "m": m * world, "n": n, "nnz": total_nnz, "sigma": info.sigma, "omega": 32, "tiles_per_gpu": info.p,
+            "m": m_total, "n": n, "nnz": total_nnz, "sigma": info.sigma, "omega": 32, "tiles_per_gpu": info.p,
             "num_packet": info.num_packet, "values": "uniform (0,1], seed 42", "l2": "inputs larger than L2 "
             f"({b_alg / 1e6:.0f} MB streamed per step vs 126 MB L2); no flush needed",
             "kernel": roofline["kernel"], "launches_per_step": launches_per_step,

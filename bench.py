@@ -261,9 +261,11 @@ def main():
     ap.add_argument("--sigma", type=int, default=-1)
     ap.add_argument("--hot", type=int, default=0, help="hot-column table: 0 off (default), -1 auto, K entries")
     ap.add_argument("--hot-threads", type=int, default=0)
+    ap.add_argument("--scheme", type=int, default=0, help="N > 1 fused modes: 0 auto, 1 stores fused into the SpMV "
+                    "kernels, 2 one coalesced push pass after the SpMV")
     ap.add_argument("--wpb", type=int, default=0, help="tuning: warps per CTA of the direct kernel")
     ap.add_argument("--nch", type=int, default=0, help="tuning: register chunks per tile")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "fused-unicast", "nccl"],
                     help="N > 1: y exchange fused into the SpMV kernels (peer stores) or NCCL all-gather after it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -295,8 +297,11 @@ def main():
     m_total = int(bounds[-1])
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     mode = args.exchange if world > 1 else "local"
-    sh = S.ShardedCsr5(bounds, n, w["row_ptr"], w["col"], w["val"], mode="fused" if mode == "fused" else "nccl",
-                       sigma=args.sigma)
+    sh = S.ShardedCsr5(bounds, n, w["row_ptr"], w["col"], w["val"], mode="nccl" if mode == "nccl" else "fused",
+                       sigma=args.sigma, multicast=None if mode == "fused" else False, scheme=args.scheme)
+    if world > 1 and mode != "nccl":
+        mode = ("fused, " + {0: "scheme auto", 1: "stores issued by the SpMV kernels", 2: "coalesced push pass after the SpMV"}
+                [args.scheme] + (", NVSwitch multicast stores" if sh.multicast else ", unicast peer stores"))
     A = sh.h   # the ordinary single-GPU handle of this rank's rows
     assert sh.setX(w["x"]) == 0
     A.set_option(H.OPT_KERNEL, args.kernel)
@@ -305,6 +310,7 @@ def main():
     A.set_option(H.OPT_CTAS_PER_SM, args.ctas_per_sm)
     A.set_option(H.OPT_HOT_COLUMNS, args.hot)
     A.set_option(H.OPT_HOT_THREADS, args.hot_threads)
+    A.set_option(H.OPT_EXCHANGE, args.scheme)
     A.set_option(H.OPT_DIRECT_WPB, args.wpb)
     A.set_option(H.OPT_DIRECT_NCH, args.nch)
     A.warmup()
@@ -401,8 +407,8 @@ def main():
         in_bytes = (m_total - m) * vb
         t_link = in_bytes / (link_gbs * 1e6)
         multi = {"exchange": mode, "ms_per_step_spmv_only_no_exchange": ms_local,
-                 "ms_per_step_spmv_then_nccl_allgather": ms_nccl, "ms_per_step_fused_peer_stores": ms_step
-                 if mode == "fused" else None,
+                 "ms_per_step_spmv_then_nccl_allgather": ms_nccl, "ms_per_step_fused": ms_step
+                 if mode.startswith("fused") else None,
                  "nvlink_inbound_bytes_per_gpu_per_step": in_bytes, "nvlink_peak_GBps_per_direction": link_gbs,
                  "nvlink_time_floor_ms": t_link,
                  "note": "every rank ends each step holding all of y: (N-1)*m*sizeof(VT) bytes must enter each "

@@ -43,7 +43,8 @@ SIGNATURES = {
     "csr5b200_as_csr5": (C.c_int, [C.c_void_p]),
     "csr5b200_set_x": (C.c_int, [C.c_void_p, C.c_void_p]),
     "csr5b200_spmv": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
-    "csr5b200_spmv_scatter": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
+    "csr5b200_spmv_scatter": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
+                                         C.c_int]),
     "csr5b200_destroy": (C.c_int, [C.c_void_p]),
     "csr5b200_set_sigma": (C.c_int, [C.c_void_p, C.c_int]),
     "csr5b200_free": (C.c_int, [C.c_void_p]),

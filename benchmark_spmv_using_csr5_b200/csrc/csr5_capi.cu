@@ -25,6 +25,8 @@ struct csr5b200_handle_s {
     // spmv_host_batch pipeline: double-buffered staging, copy streams, events
     void *xb[2] = {nullptr, nullptr}, *yb[2] = {nullptr, nullptr};
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    // sharded mode (spmv_scatter)
+    ShardCtx shard;
     cudaEvent_t e_in[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
     int kernel_timing = 0;
     std::vector<cudaEvent_t> ev;  // begin/end pairs of the timed main kernels
@@ -227,6 +229,10 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
         case CSR5B200_OPT_HOT_COLUMNS: h->tune.hot_columns = value; break;
         case CSR5B200_OPT_HOT_THREADS: h->tune.hot_threads = value; break;
+        case CSR5B200_OPT_EXCHANGE:
+            if (value < 0 || value > 2) return CSR5B200_INVALID_ARGUMENT;
+            h->tune.exchange = value;
+            break;
         default: return CSR5B200_INVALID_ARGUMENT;
     }
     return CSR5B200_SUCCESS;
@@ -336,12 +342,13 @@ int csr5b200_as_csr(csr5b200_handle_t h)
     return CSR5B200_SUCCESS;
 }
 
-static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void *const *y_dst)
+static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void *const *y_dst, int multicast)
 {
+    const ShardCtx *sh = nullptr;
     if (!h) return CSR5B200_INVALID_ARGUMENT;
     if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_UNSUPPORTED_CSR_SPMV;
     if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
-    if ((n_dst == 0 && !y && h->pl.m > 0) || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
+    if ((!y && h->pl.m > 0) || (!h->pl.x && h->pl.nnz > 0)) return CSR5B200_INVALID_ARGUMENT;
     if (n_dst < 0 || n_dst > CSR5B200_MAX_SCATTER || (n_dst > 0 && !y_dst)) return CSR5B200_INVALID_ARGUMENT;
     for (int k = 0; k < n_dst; k++)
         if (!y_dst[k]) return CSR5B200_INVALID_ARGUMENT;
@@ -358,22 +365,31 @@ static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void
         h->tune.ev_end = h->ev[h->ev_used + 1];
         h->ev_used += 2;
     }
+    if (n_dst > 0) {
+        ShardCtx &s = h->shard;
+        s.n_dst = n_dst;
+        s.y_dst = y_dst;
+        s.multicast = multicast;
+        s.exchange = h->tune.exchange;
+        sh = &s;
+    }
     if (h->pl.value_bytes == 8)
-        e = launch_spmv_f64(h->pl, h->tune, alpha, static_cast<double *>(y), n_dst, y_dst, h->stream,
-                            &h->kernel_in_use, &h->launches_per_spmv);
+        e = launch_spmv_f64(h->pl, h->tune, alpha, static_cast<double *>(y), sh, h->stream, &h->kernel_in_use,
+                            &h->launches_per_spmv);
     else
-        e = launch_spmv_f32(h->pl, h->tune, (float)alpha, static_cast<float *>(y), n_dst, y_dst, h->stream,
+        e = launch_spmv_f32(h->pl, h->tune, (float)alpha, static_cast<float *>(y), sh, h->stream,
                             &h->kernel_in_use, &h->launches_per_spmv);
     if (e != cudaSuccess) return cuda_fail(h, e);
     return CSR5B200_SUCCESS;
 }
 
-int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y) { return spmv_impl(h, alpha, y, 0, nullptr); }
+int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y) { return spmv_impl(h, alpha, y, 0, nullptr, 0); }
 
-int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, int n_dst, void *const *y_dst)
+int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, void *y_local, int n_dst, void *const *y_dst,
+                          int dst_is_multicast)
 {
-    if (n_dst < 1) return CSR5B200_INVALID_ARGUMENT;
-    return spmv_impl(h, alpha, nullptr, n_dst, y_dst);
+    if (n_dst < 1 || (dst_is_multicast && n_dst != 1)) return CSR5B200_INVALID_ARGUMENT;
+    return spmv_impl(h, alpha, y_local, n_dst, y_dst, dst_is_multicast ? 1 : 0);
 }
 
 int csr5b200_destroy(csr5b200_handle_t h)
@@ -395,6 +411,7 @@ int csr5b200_destroy(csr5b200_handle_t h)
         if (h->e_out[b]) cudaEventDestroy(h->e_out[b]);
         h->e_in[b] = h->e_comp[b] = h->e_out[b] = nullptr;
     }
+    h->shard = ShardCtx();
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     h->s_in = h->s_out = nullptr;

@@ -58,6 +58,7 @@ struct SpmvTuning {
     int direct_nch = 0;    // tuning: register chunks per tile (0 = default rule)
     int hot_columns = 0;   // 0 off (default), -1 auto (kept if it serves >= 25 % of the references), > 0 capacity
     int hot_threads = 0;   // tuning: threads per CTA of the hot-column kernel (0 = default)
+    int exchange = 0;      // sharded mode: 0 auto, 1 fused, 2 push
     cudaEvent_t ev_begin = nullptr;  // optional: recorded right before / after the main SpMV kernel
     cudaEvent_t ev_end = nullptr;
 };
@@ -84,13 +85,21 @@ cudaError_t launch_transpose(const Plan &pl, bool r2c, cudaStream_t stream);
 cudaError_t launch_warmup(cudaStream_t stream);
 
 // ---- SpMV (csr5_spmv_f64.cu / csr5_spmv_f32.cu via csr5_spmv.cuh) -----------------------------
-// Enqueues [clear y] + compute(+tail) + calibrate.  Returns the kernel variant used in *used.
-// n_dst == 0: y is the (local) result vector.  n_dst > 0: y is ignored and every value is stored to
-// y_dst[0..n_dst) instead (sharded mode: this rank's segment inside each peer's concatenated y).
-cudaError_t launch_spmv_f64(const Plan &pl, const SpmvTuning &tn, double alpha, double *y, int n_dst,
-                            void *const *y_dst, cudaStream_t stream, int *used, int *launches);
-cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, int n_dst,
-                            void *const *y_dst, cudaStream_t stream, int *used, int *launches);
+// Sharded (multi-GPU) mode of one spmv() (csr5b200_spmv_scatter): where the rows go besides local HBM.
+struct ShardCtx {
+    int n_dst = 0;
+    void *const *y_dst = nullptr;   // this rank's segment inside each GPU's concatenated y, or one multicast address
+    int multicast = 0;
+    int exchange = 0;               // 0 auto, 1 fused (SpMV kernels store to every destination), 2 push (copy pass after)
+};
+
+// Enqueues [clear y] + compute(+tail) + calibrate; in sharded mode (sh != nullptr) the rows are also
+// delivered to every destination (fused into the kernels, or by a copy pass).  y is the result vector in local memory.  Returns the
+// kernel variant used in *used.
+cudaError_t launch_spmv_f64(const Plan &pl, const SpmvTuning &tn, double alpha, double *y, const ShardCtx *sh,
+                            cudaStream_t stream, int *used, int *launches);
+cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, const ShardCtx *sh,
+                            cudaStream_t stream, int *used, int *launches);
 
 }  // namespace csr5
 

@@ -54,36 +54,41 @@ struct SpmvArgs {
     int tail_start;      // first row of the tail tile
     int tail_nnz_start;  // (p - 1) * omega * sigma
     int tail_warps;      // ceil((m - tail_start) / 32)
-    // Sharded (multi-GPU) mode: every y value is stored to n_dst destination segments instead of y --
-    // this rank's slot in each peer's concatenated y, mapped over NVLink (csr5b200_spmv_scatter).
+    // Sharded (multi-GPU) mode (csr5b200_spmv_scatter): `y` is this rank's segment in local HBM; the
+    // n_dst destination segments -- this rank's slot in each GPU's concatenated y, mapped over NVLink,
+    // or ONE NVSwitch multicast address that replicates a store to all of them -- receive copies.
     int n_dst;
+    int dst_multicast;   // 1: y_dst[0] is a multicast (multimem) address
     VT *y_dst[CSR5B200_MAX_SCATTER];
 };
 
-// All y traffic of the kernels goes through these two helpers.  MULTI = false: the plain local
-// store / reduction.  MULTI = true: the store is replicated to every destination (fused all-gather:
-// peer stores ride NVLink while the tile stream keeps HBM busy).
+template <typename VT> __device__ __forceinline__ void multimem_store(VT *p, VT v);
+template <> __device__ __forceinline__ void multimem_store<double>(double *p, double v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+template <> __device__ __forceinline__ void multimem_store<float>(float *p, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// All y stores of the SpMV kernels go through put_y.  MULTI = false: the plain local store.  MULTI = true
+// (sharded mode, "fused" exchange): the value is stored to every destination instead -- each GPU's copy
+// of the concatenated y over NVLink, or once to the NVSwitch multicast address -- so the all-gather
+// traffic rides along with the tile stream.
 template <bool MULTI, typename VT>
 __device__ __forceinline__ void put_y(const SpmvArgs<VT> &a, int row, VT v)
 {
     if constexpr (!MULTI) {
         a.y[row] = v;
     } else {
+        if (a.dst_multicast) {
+            multimem_store<VT>(a.y_dst[0] + row, v);
+        } else {
 #pragma unroll
-        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
-            if (k < a.n_dst) a.y_dst[k][row] = v;
-    }
-}
-
-template <bool MULTI, typename VT>
-__device__ __forceinline__ void add_y(const SpmvArgs<VT> &a, int row, VT v)
-{
-    if constexpr (!MULTI) {
-        atomicAdd(a.y + row, v);
-    } else {
-#pragma unroll
-        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
-            if (k < a.n_dst) atomicAdd(a.y_dst[k] + row, v);  // red.global.add, also over NVLink
+            for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+                if (k < a.n_dst) a.y_dst[k][row] = v;
+        }
     }
 }
 
@@ -313,7 +318,8 @@ __global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT
     const int t = (int)tl;
     const size_t base = (size_t)t * (OMEGA * SIGMA);
     GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet};
-    process_tile<VT, SIGMA, MULTI, GlobalTile<VT>, NCH>(a, tile, t, lane, __ldg(a.tile_ptr + t), __ldg(a.tile_ptr + t + 1));
+    process_tile<VT, SIGMA, MULTI, GlobalTile<VT>, NCH>(a, tile, t, lane, __ldg(a.tile_ptr + t),
+                                                        __ldg(a.tile_ptr + t + 1));
 }
 
 // ---- TMA-staged persistent kernel ---------------------------------------------------------------
@@ -503,27 +509,112 @@ spmv_hot_kernel(const SpmvArgs<VT> a, const VT *__restrict__ hot_x, const uint32
 }
 
 // ---- carries: y[row of tile t] += calibrator[t] for the tiles whose first row began earlier -----
-template <typename VT, bool MULTI>
+template <typename VT>
 __global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.p) return;
     const VT c = a.cal[t];
-    if (c != (VT)0) add_y<MULTI, VT>(a, (int)(a.tile_ptr[t] & ROW_MASK), c);
+    if (c != (VT)0) atomicAdd(a.y + (a.tile_ptr[t] & ROW_MASK), c);   // local HBM only, also when sharded
 }
 
-// sharded mode only: rows no tile stores (empty rows) are cleared in every destination
+// ---- sharded mode, "push" exchange: copy this rank's finished y segment to every destination ----------
+// One coalesced pass after the SpMV and its carry pass: 16-byte loads from local HBM, 16-byte stores over
+// NVLink to each peer or once to the NVSwitch multicast address (which replicates them in the switch).
+// NVLink only ever sees wide coalesced writes, whatever the row structure of the matrix.
 template <typename VT>
-__global__ void __launch_bounds__(256) zero_rows_kernel(const SpmvArgs<VT> a)
+struct PushArgs {
+    const VT *y_local;
+    VT *dst[CSR5B200_MAX_SCATTER];
+    int n_dst, multicast, m;
+};
+
+template <typename VT> __device__ __forceinline__ void push_store16(const PushArgs<VT> &a, size_t elem, int4 v)
+{
+    if (a.multicast) {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dst[0] + elem),
+                     "f"(__int_as_float(v.x)), "f"(__int_as_float(v.y)), "f"(__int_as_float(v.z)),
+                     "f"(__int_as_float(v.w)) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+            if (k < a.n_dst && a.dst[k] != a.y_local) *reinterpret_cast<int4 *>(a.dst[k] + elem) = v;
+    }
+}
+
+template <typename VT> __device__ __forceinline__ void push_store1(const PushArgs<VT> &a, size_t elem, VT v)
+{
+    if (a.multicast) {
+        multimem_store<VT>(a.dst[0] + elem, v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+            if (k < a.n_dst && a.dst[k] != a.y_local) a.dst[k][elem] = v;
+    }
+}
+
+constexpr int PUSH_THREADS = 256;
+
+template <typename VT>
+__global__ void __launch_bounds__(PUSH_THREADS) push_rows_kernel(const PushArgs<VT> a)
+{
+    constexpr int VEC = 16 / (int)sizeof(VT);
+    const size_t n = (size_t)a.m;
+    // scalar head up to a 16-byte boundary (all destinations share the local segment's alignment)
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(a.y_local) & 15)) & 15) / sizeof(VT);
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / VEC;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    if (gtid < head) push_store1<VT>(a, gtid, a.y_local[gtid]);
+    const int4 *src = reinterpret_cast<const int4 *>(a.y_local + head);
+    size_t i = gtid;
+    for (; i + 3 * gsz < nvec; i += 4 * gsz) {   // four 16-byte loads in flight per thread before their stores
+        const int4 v0 = src[i], v1 = src[i + gsz], v2 = src[i + 2 * gsz], v3 = src[i + 3 * gsz];
+        push_store16<VT>(a, head + i * VEC, v0);
+        push_store16<VT>(a, head + (i + gsz) * VEC, v1);
+        push_store16<VT>(a, head + (i + 2 * gsz) * VEC, v2);
+        push_store16<VT>(a, head + (i + 3 * gsz) * VEC, v3);
+    }
+    for (; i < nvec; i += gsz) push_store16<VT>(a, head + i * VEC, src[i]);
+    const size_t done_elems = head + nvec * VEC;
+    if (gtid < n - done_elems) push_store1<VT>(a, done_elems + gtid, a.y_local[done_elems + gtid]);
+}
+
+// sharded mode, "fused" exchange: rows no tile stores (= the empty rows) are cleared in every destination
+template <typename VT>
+__global__ void __launch_bounds__(256) zero_empty_rows_kernel(const SpmvArgs<VT> a)
 {
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.m; r += (long long)gridDim.x * blockDim.x)
-        put_y<true, VT>(a, (int)r, (VT)0);
+        if (__ldg(a.row_ptr + r) == __ldg(a.row_ptr + r + 1)) put_y<true, VT>(a, (int)r, (VT)0);
+}
+
+// sharded mode, "fused" exchange: rows that received carries are complete in local HBM only after
+// calibrate_kernel; the last tile of each such row re-sends the final value to every destination (plain
+// stores -- no atomics cross NVLink).
+template <typename VT>
+__global__ void __launch_bounds__(256) push_carried_rows_kernel(const SpmvArgs<VT> a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.p) return;
+    const uint32_t r = a.tile_ptr[t] & ROW_MASK;
+    const bool last = t == a.p - 1 || (a.tile_ptr[t + 1] & ROW_MASK) != r;
+    if (!last || r >= (uint32_t)a.m) return;
+    const bool carried = a.cal[t] != (VT)0 || (t > 0 && (a.tile_ptr[t - 1] & ROW_MASK) == r);
+    if (!carried) return;
+    const VT v = a.y[r];
+    if (a.dst_multicast) {
+        multimem_store<VT>(a.y_dst[0] + r, v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+            if (k < a.n_dst && a.y_dst[k] != a.y) a.y_dst[k][r] = v;
+    }
 }
 
 // ---- host-side dispatch ----------------------------------------------------------------------------
 template <typename VT, int SIGMA>
 cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_ok, cudaStream_t stream,
-                         int *used, int hot_k, const VT *hot_x)
+                         int *used, int hot_k, const VT *hot_x, bool multi)
 {
     const long long ntiles = a.p - 1;
     if (hot_k > 0 && ntiles > 0) {
@@ -542,19 +633,19 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
         };
         *used = 3;
         if constexpr (SIGMA == 15 || SIGMA == 16) {
-            if (a.n_dst == 0 && tn.direct_nch == 1) return run(spmv_hot_kernel<VT, SIGMA, false, 1>);
-            if (a.n_dst == 0 && tn.direct_nch == 2) return run(spmv_hot_kernel<VT, SIGMA, false, 2>);
-            if (a.n_dst == 0 && tn.direct_nch == 3) return run(spmv_hot_kernel<VT, SIGMA, false, 3>);
-            if (a.n_dst == 0 && tn.direct_nch == 4) return run(spmv_hot_kernel<VT, SIGMA, false, 4>);
+            if (!multi && tn.direct_nch == 1) return run(spmv_hot_kernel<VT, SIGMA, false, 1>);
+            if (!multi && tn.direct_nch == 2) return run(spmv_hot_kernel<VT, SIGMA, false, 2>);
+            if (!multi && tn.direct_nch == 3) return run(spmv_hot_kernel<VT, SIGMA, false, 3>);
+            if (!multi && tn.direct_nch == 4) return run(spmv_hot_kernel<VT, SIGMA, false, 4>);
         }
-        return a.n_dst > 0 ? run(spmv_hot_kernel<VT, SIGMA, true>) : run(spmv_hot_kernel<VT, SIGMA, false>);
+        return multi ? run(spmv_hot_kernel<VT, SIGMA, true>) : run(spmv_hot_kernel<VT, SIGMA, false>);
     }
     int kernel = tn.kernel;
     // auto = direct-load: on B200 it streams C2 at 98 % of the measured HBM copy bandwidth vs 87 % for
     // the TMA-staged ring (profiles/r01_*; the ring's few, fat warps expose the x-gather latency).
     if (kernel == 0) kernel = 1;
     if (kernel == 2 && !tma_ok) kernel = 1;
-    if (ntiles <= 0 || a.n_dst > 0) kernel = 1;  // the scatter (sharded) variant exists for the direct kernel
+    if (ntiles <= 0 || multi) kernel = 1;  // the multi-destination (sharded) variant exists for the direct kernel
     *used = kernel;
 
     if (kernel == 1) {
@@ -563,7 +654,7 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
         // tuning variants (CSR5B200_OPT_DIRECT_WPB / _NCH), instantiated for the sigmas of the benchmark
         // configurations only; everything else uses the default shape
         if constexpr (SIGMA == 15 || SIGMA == 16 || SIGMA == 26) {
-            if (a.n_dst == 0 && (tn.direct_wpb > 0 || tn.direct_nch > 0)) {
+            if (!multi && (tn.direct_wpb > 0 || tn.direct_nch > 0)) {
                 const int wpb = tn.direct_wpb > 0 ? tn.direct_wpb : 4;
                 const int nch = tn.direct_nch > 0 ? tn.direct_nch : ChunkOf<VT, SIGMA, 0>::N;
 #define CSR5_VARIANT(W, N)                                                                                   \
@@ -581,7 +672,7 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
         }
         constexpr int WPB = 4;
         const long long blocks = (units + WPB - 1) / WPB;
-        if (a.n_dst > 0) spmv_direct_kernel<VT, SIGMA, WPB, true><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
+        if (multi) spmv_direct_kernel<VT, SIGMA, WPB, true><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
         else spmv_direct_kernel<VT, SIGMA, WPB, false><<<(unsigned)blocks, WPB * 32, 0, stream>>>(a);
         return cudaGetLastError();
     }
@@ -618,30 +709,27 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
 }
 
 template <typename VT>
-cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y, int n_dst, void *const *y_dst,
+cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y, const ShardCtx *sh,
                           cudaStream_t stream, int *used, int *launches)
 {
     *used = 0;
     *launches = 0;
     if (pl.m <= 0) return cudaSuccess;
+    const int n_dst = sh ? sh->n_dst : 0;
     if (n_dst < 0 || n_dst > CSR5B200_MAX_SCATTER) return cudaErrorInvalidValue;
+    // exchange of the sharded mode: fused = the SpMV kernels store to every destination; push = one coalesced
+    // copy pass after the SpMV.  Auto: fused when each tile stores runs of consecutive rows (no empty rows,
+    // short rows), push when the row stores are scattered (dirty tiles, long rows).
+    int exchange = sh ? sh->exchange : 0;
+    if (sh && exchange == 0)
+        exchange = (!pl.needs_zero_fill && pl.m > 0 && (long long)pl.nnz / pl.m <= 64) ? 1 : 2;
+    const bool fused = exchange == 1;
     cudaError_t e;
     SpmvArgs<VT> a;
     a.n_dst = n_dst;
-    for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) a.y_dst[k] = k < n_dst ? static_cast<VT *>(y_dst[k]) : nullptr;
-    a.m = pl.m;
-    if (pl.needs_zero_fill || pl.p == 0) {
-        if (n_dst > 0) {
-            a.y = nullptr;
-            zero_rows_kernel<VT><<<tn.num_sms * 8, 256, 0, stream>>>(a);
-            e = cudaGetLastError();
-        } else {
-            e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
-        }
-        if (e != cudaSuccess) return e;
-        ++*launches;
-        if (pl.p == 0) return cudaSuccess;
-    }
+    a.dst_multicast = sh ? sh->multicast : 0;
+    for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+        a.y_dst[k] = k < n_dst ? static_cast<VT *>(sh->y_dst[k]) : nullptr;
     a.row_ptr = pl.row_ptr;
     a.col = pl.col;
     a.val = static_cast<const VT *>(pl.val);
@@ -659,38 +747,62 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
     a.bit_all = pl.bit_y + pl.bit_ss;
     a.num_packet = pl.num_packet;
     a.tail_start = pl.tail_start;
-    a.tail_nnz_start = (pl.p - 1) * OMEGA * pl.sigma;
-    a.tail_warps = (pl.m - pl.tail_start + 31) / 32;
+    a.tail_nnz_start = pl.p > 0 ? (pl.p - 1) * OMEGA * pl.sigma : 0;
+    a.tail_warps = pl.p > 0 ? (pl.m - pl.tail_start + 31) / 32 : 0;
 
-    // bulk TMA needs 16-byte aligned global addresses; tile strides are multiples of 128 bytes
-    const bool tma_ok = (reinterpret_cast<uintptr_t>(a.val) % 16 == 0) &&
-                        (reinterpret_cast<uintptr_t>(a.col) % 16 == 0) &&
-                        (reinterpret_cast<uintptr_t>(a.desc) % 16 == 0);
-
-    if (pl.hot_k > 0 && pl.p > 1) {
-        hot_gather_kernel<VT><<<(pl.hot_k + 255) / 256, 256, 0, stream>>>(a.x, pl.hot_col, static_cast<VT *>(pl.hot_x),
-                                                                        pl.hot_k);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (pl.needs_zero_fill || pl.p == 0) {
+        if (fused) {
+            zero_empty_rows_kernel<VT><<<tn.num_sms * 8, 256, 0, stream>>>(a);
+            e = cudaGetLastError();
+        } else {
+            e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
+        }
+        if (e != cudaSuccess) return e;
         ++*launches;
     }
-    if (tn.ev_begin && (e = cudaEventRecord(tn.ev_begin, stream)) != cudaSuccess) return e;
-    switch (pl.sigma) {
-#define CSR5_CASE(S) case S: e = launch_sigma<VT, S>(a, tn, tma_ok, stream, used, pl.hot_k, static_cast<const VT *>(pl.hot_x)); break;
-        CSR5_CASE(4) CSR5_CASE(5) CSR5_CASE(6) CSR5_CASE(7) CSR5_CASE(8) CSR5_CASE(9) CSR5_CASE(10)
-        CSR5_CASE(11) CSR5_CASE(12) CSR5_CASE(13) CSR5_CASE(14) CSR5_CASE(15) CSR5_CASE(16)
-        CSR5_CASE(17) CSR5_CASE(18) CSR5_CASE(19) CSR5_CASE(20) CSR5_CASE(21) CSR5_CASE(22)
-        CSR5_CASE(23) CSR5_CASE(24) CSR5_CASE(25) CSR5_CASE(26) CSR5_CASE(27) CSR5_CASE(28)
-        CSR5_CASE(29) CSR5_CASE(30) CSR5_CASE(31) CSR5_CASE(32)
+    if (pl.p > 0) {
+        // bulk TMA needs 16-byte aligned global addresses; tile strides are multiples of 128 bytes
+        const bool tma_ok = (reinterpret_cast<uintptr_t>(a.val) % 16 == 0) &&
+                            (reinterpret_cast<uintptr_t>(a.col) % 16 == 0) &&
+                            (reinterpret_cast<uintptr_t>(a.desc) % 16 == 0);
+        if (pl.hot_k > 0 && pl.p > 1) {
+            hot_gather_kernel<VT><<<(pl.hot_k + 255) / 256, 256, 0, stream>>>(a.x, pl.hot_col,
+                                                                            static_cast<VT *>(pl.hot_x), pl.hot_k);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            ++*launches;
+        }
+        if (tn.ev_begin && (e = cudaEventRecord(tn.ev_begin, stream)) != cudaSuccess) return e;
+        switch (pl.sigma) {
+#define CSR5_CASE(S) case S: e = launch_sigma<VT, S>(a, tn, tma_ok, stream, used, pl.hot_k, static_cast<const VT *>(pl.hot_x), fused); break;
+            CSR5_CASE(4) CSR5_CASE(5) CSR5_CASE(6) CSR5_CASE(7) CSR5_CASE(8) CSR5_CASE(9) CSR5_CASE(10)
+            CSR5_CASE(11) CSR5_CASE(12) CSR5_CASE(13) CSR5_CASE(14) CSR5_CASE(15) CSR5_CASE(16)
+            CSR5_CASE(17) CSR5_CASE(18) CSR5_CASE(19) CSR5_CASE(20) CSR5_CASE(21) CSR5_CASE(22)
+            CSR5_CASE(23) CSR5_CASE(24) CSR5_CASE(25) CSR5_CASE(26) CSR5_CASE(27) CSR5_CASE(28)
+            CSR5_CASE(29) CSR5_CASE(30) CSR5_CASE(31) CSR5_CASE(32)
 #undef CSR5_CASE
-        default: return cudaErrorInvalidValue;
+            default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+        if (tn.ev_end && (e = cudaEventRecord(tn.ev_end, stream)) != cudaSuccess) return e;
+        ++*launches;
+        const int threads = 256;
+        calibrate_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);   // local HBM only
+        ++*launches;
+        if (fused) {
+            push_carried_rows_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);
+            ++*launches;
+        }
     }
-    if (e != cudaSuccess) return e;
-    if (tn.ev_end && (e = cudaEventRecord(tn.ev_end, stream)) != cudaSuccess) return e;
-    ++*launches;
-    const int threads = 256;
-    if (n_dst > 0) calibrate_kernel<VT, true><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);
-    else calibrate_kernel<VT, false><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);
-    ++*launches;
+    if (sh && !fused) {
+        PushArgs<VT> pa;
+        pa.y_local = y;
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) pa.dst[k] = a.y_dst[k];
+        pa.n_dst = n_dst;
+        pa.multicast = a.dst_multicast;
+        pa.m = pl.m;
+        push_rows_kernel<VT><<<tn.num_sms * 4, PUSH_THREADS, 0, stream>>>(pa);
+        ++*launches;
+    }
     return cudaGetLastError();
 }
 

@@ -2,9 +2,9 @@
 #include "csr5_spmv.cuh"
 
 namespace csr5 {
-cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, int n_dst,
-                            void *const *y_dst, cudaStream_t stream, int *used, int *launches)
+cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, const ShardCtx *sh,
+                            cudaStream_t stream, int *used, int *launches)
 {
-    return launch_spmv_t<float>(pl, tn, alpha, y, n_dst, y_dst, stream, used, launches);
+    return launch_spmv_t<float>(pl, tn, alpha, y, sh, stream, used, launches);
 }
 }  // namespace csr5

@@ -47,6 +47,8 @@ OPT_DIRECT_WPB = 7
 OPT_DIRECT_NCH = 8
 OPT_HOT_COLUMNS = 9
 OPT_HOT_THREADS = 10
+OPT_EXCHANGE = 11
+EXCHANGE_AUTO, EXCHANGE_FUSED, EXCHANGE_PUSH = 0, 1, 2
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_HOT = 0, 1, 2, 3
 
 
@@ -116,12 +118,14 @@ class anonymouslibHandle:
         self._bind_stream()
         return self._lib.csr5b200_spmv(self._h, float(alpha), _ptr(y))
 
-    def spmv_scatter(self, alpha: float, y_dst, n_dst: int) -> int:
-        """Sharded mode: ``y_dst`` is a ctypes array of ``n_dst`` device pointers, each the address of
-        this shard's first row inside one destination's concatenated y (csr5b200_spmv_scatter)."""
+    def spmv_scatter(self, alpha: float, y_local, y_dst, n_dst: int, multicast: bool = False) -> int:
+        """Sharded mode (csr5b200_spmv_scatter): ``y_local`` is this shard's y segment (CUDA tensor in local
+        memory), ``y_dst`` a ctypes array of ``n_dst`` device pointers, each the address of this shard's
+        first row inside one destination's concatenated y -- or one multicast address."""
+        _check_dev(y_local, self.dtype, "y_local", self.m)
         self._bind_stream()
-        return self._lib.csr5b200_spmv_scatter(self._h, float(alpha), int(n_dst),
-                                               C.cast(y_dst, C.POINTER(C.c_void_p)))
+        return self._lib.csr5b200_spmv_scatter(self._h, float(alpha), _ptr(y_local), int(n_dst),
+                                               C.cast(y_dst, C.POINTER(C.c_void_p)), 1 if multicast else 0)
 
     def destroy(self) -> int:
         if not self._h:

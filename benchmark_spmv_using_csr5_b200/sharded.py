@@ -10,9 +10,13 @@ ordinary handle, x is replicated, and the y segments are concatenated on every r
 Two exchange modes:
 
 * ``"fused"`` (default): the concatenated y lives in symmetric memory (every rank's buffer mapped
-  into every process over NVLink/NVSwitch).  The SpMV kernels store each finished row to ALL
-  destinations as tiles complete (``csr5b200_spmv_scatter``), so the all-gather traffic overlaps the
-  tile stream; one device-side barrier ends the step.  No NCCL call on the data path.
+  into every process over NVLink/NVSwitch) and ``csr5b200_spmv_scatter`` delivers this rank's rows to
+  ALL of them -- through ONE store to the NVSwitch multicast address when the fabric offers it
+  (``multicast=True``, the default when available), else through one store per peer.  ``scheme`` 1:
+  the SpMV kernels themselves store each finished row to the destinations as tiles complete, so the
+  all-gather traffic overlaps the tile stream; ``scheme`` 2: the SpMV runs on local memory and one
+  coalesced pass pushes the segment (16-byte stores); 0 = auto by row structure.  One device-side
+  barrier ends the step.  No NCCL call on the data path.
 * ``"nccl"``: local SpMV into this rank's slot, then an all-gather(-v) over NCCL (the baseline the
   fused mode is measured against; also what runs on gloo in the CPU tests of the host logic).
 """
@@ -92,7 +96,7 @@ class ShardedCsr5:
     the G + 1 global row boundaries (``row_partition``); ``n`` is the global column count."""
 
     def __init__(self, bounds, n: int, local_row_ptr, col, val, group=None, mode: str = "fused",
-                 sigma: int = -1):
+                 sigma: int = -1, multicast: bool | None = None, scheme: int = 0):
         import torch
         import torch.distributed as dist
         from . import handle as H
@@ -116,16 +120,23 @@ class ShardedCsr5:
         if err:
             raise RuntimeError(self.h.error_string(err))
         self.h.setSigma(sigma)
+        self.h.set_option(H.OPT_EXCHANGE, scheme)   # 0 auto, 1 stores fused into the SpMV kernels, 2 push pass
         self._symm = None
         self._dst = None
+        self.multicast = False
         dev = val.device
         if mode == "fused" and self.world > 1:
             import torch.distributed._symmetric_memory as symm_mem
             self.y_full = symm_mem.empty(self.m_global, dtype=self.dtype, device=dev)
             self._symm = symm_mem.rendezvous(self.y_full, group if group is not None else dist.group.WORLD)
             item = self.y_full.element_size()
-            ptrs = [int(p) + self.row_begin * item for p in self._symm.buffer_ptrs]
-            self._dst = (C.c_void_p * self.world)(*ptrs)
+            mc = int(self._symm.multicast_ptr or 0)
+            self.multicast = bool(mc) if multicast is None else (bool(multicast) and bool(mc))
+            if self.multicast:
+                self._dst = (C.c_void_p * 1)(mc + self.row_begin * item)
+            else:
+                ptrs = [int(p) + self.row_begin * item for p in self._symm.buffer_ptrs]
+                self._dst = (C.c_void_p * self.world)(*ptrs)
         else:
             self.y_full = torch.empty(self.m_global, dtype=self.dtype, device=dev)
         self.y_local = self.y_full[self.row_begin:self.row_end]
@@ -146,7 +157,7 @@ class ShardedCsr5:
         if self.world == 1:
             err = self.h.spmv(alpha, self.y_local)
         elif self._dst is not None:
-            err = self.h.spmv_scatter(alpha, self._dst, self.world)
+            err = self.h.spmv_scatter(alpha, self.y_local, self._dst, len(self._dst), self.multicast)
             if not err:
                 self._symm.barrier(channel=0)  # all peers' stores have landed before anyone reads y
         else:

@@ -88,14 +88,24 @@ CSR5B200_API int csr5b200_set_sigma(csr5b200_handle_t h, int sigma);
 
 #define CSR5B200_MAX_SCATTER 8
 
-/* spmv() of a row-range shard whose result is written to n_dst destinations at once: y_dst[k] is the
- * address of THIS shard's first row inside destination k's concatenated y (device pointers; peers'
- * buffers mapped into this process over NVLink, e.g. CUDA IPC / symmetric memory; the local buffer is
- * simply one of them).  Fuses the all-gather of the y segments into the SpMV kernels: finished rows
- * are stored to every destination as tiles complete, carries use red.global.add on every destination.
- * The caller synchronises the devices afterwards (a cross-GPU barrier) before anyone reads y.
+/* spmv() of a row-range shard that also delivers the result to the other GPUs -- the all-gather of the
+ * y segments fused into the SpMV kernels.
+ *   y_local : this shard's y segment in LOCAL device memory; carries are accumulated here, and on return of
+ *             the enqueued work it holds the final rows like after spmv().
+ *   y_dst[k]: address of THIS shard's first row inside destination k's concatenated y (device pointers;
+ *             peers' buffers mapped into this process over NVLink, e.g. CUDA IPC / symmetric memory).  The
+ *             list normally contains y_local itself.  With dst_is_multicast = 1, n_dst must be 1 and
+ *             y_dst[0] is an NVSwitch multicast address (multimem) covering all GPUs including this one.
+ * Two exchange schemes (CSR5B200_OPT_EXCHANGE): "fused" -- the SpMV kernels store every finished row to all
+ * destinations as tiles complete, so the NVLink traffic overlaps the tile stream; rows completed by carries
+ * are re-sent once after the local carry pass (plain stores only -- no atomics cross NVLink), empty rows are
+ * cleared everywhere; "push" -- the SpMV runs on local memory and one coalesced pass then copies the segment
+ * to every destination with 16-byte stores (for matrices whose row stores are scattered).  Auto picks fused
+ * for matrices without empty rows and with short rows.  Everything is ordered on the handle's stream; the
+ * caller synchronises the devices afterwards (a cross-GPU barrier) before anyone reads y.
  * 1 <= n_dst <= CSR5B200_MAX_SCATTER.  Same return codes as spmv(). */
-CSR5B200_API int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, int n_dst, void *const *y_dst);
+CSR5B200_API int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, void *y_local, int n_dst,
+                                       void *const *y_dst, int dst_is_multicast);
 
 /* Frees the handle object itself (the reference's handle is a stack object). Calls destroy(). */
 CSR5B200_API int csr5b200_free(csr5b200_handle_t h);
@@ -118,6 +128,8 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
                                          serves >= 25 % of the x references), K > 0 = table capacity in entries.
                                          While it is on, the tagged occurrences in `col` read (bit 31 | slot). */
 #define CSR5B200_OPT_HOT_THREADS   10 /* tuning: threads per CTA of the hot-column kernel (0 = default 768) */
+#define CSR5B200_OPT_EXCHANGE      11 /* spmv_scatter: 0 auto (default), 1 fused (the SpMV kernels store every finished row to
+                                         all destinations), 2 push (one coalesced copy pass after the SpMV) */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays

@@ -28,10 +28,13 @@ def main():
             y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
             bounds = S.row_partition(A.row_ptr, world)
             rp, ci, v = S.shard_csr(A.row_ptr, A.col, val, bounds[rank], bounds[rank + 1])
-            for mode in ("fused", "nccl"):
+            for mode in ("fused-multicast-1", "fused-unicast-1", "fused-multicast-2", "fused-unicast-2",
+                         "fused-multicast-0", "nccl"):
                 sh = S.ShardedCsr5(bounds, A.n, torch.from_numpy(np.ascontiguousarray(rp)).cuda(),
                                    torch.from_numpy(np.ascontiguousarray(ci)).cuda(),
-                                   torch.from_numpy(np.ascontiguousarray(v)).cuda(), mode=mode, sigma=sigma)
+                                   torch.from_numpy(np.ascontiguousarray(v)).cuda(),
+                                   mode="nccl" if mode == "nccl" else "fused", sigma=sigma,
+                                   multicast="multicast" in mode, scheme=int(mode[-1]) if mode != "nccl" else 0)
                 sh.setX(torch.from_numpy(x).cuda())
                 assert sh.asCSR5() == 0
                 sh.y_full.fill_(float("nan"))

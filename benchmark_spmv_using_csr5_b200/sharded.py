@@ -120,7 +120,8 @@ class ShardedCsr5:
         if err:
             raise RuntimeError(self.h.error_string(err))
         self.h.setSigma(sigma)
-        self.h.set_option(H.OPT_EXCHANGE, scheme)   # 0 auto, 1 stores fused into the SpMV kernels, 2 push pass
+        self.scheme = int(scheme)   # 0 auto, 1 stores fused into the SpMV kernels, 2 coalesced push pass
+        self._resolved = False
         self._symm = None
         self._dst = None
         self.multicast = False
@@ -131,12 +132,11 @@ class ShardedCsr5:
             self._symm = symm_mem.rendezvous(self.y_full, group if group is not None else dist.group.WORLD)
             item = self.y_full.element_size()
             mc = int(self._symm.multicast_ptr or 0)
-            self.multicast = bool(mc) if multicast is None else (bool(multicast) and bool(mc))
-            if self.multicast:
-                self._dst = (C.c_void_p * 1)(mc + self.row_begin * item)
-            else:
-                ptrs = [int(p) + self.row_begin * item for p in self._symm.buffer_ptrs]
-                self._dst = (C.c_void_p * self.world)(*ptrs)
+            ptrs = [int(p) + self.row_begin * item for p in self._symm.buffer_ptrs]
+            self._dst_unicast = (C.c_void_p * self.world)(*ptrs)
+            self._dst_multicast = (C.c_void_p * 1)(mc + self.row_begin * item) if mc else None
+            self._want_multicast = multicast   # None = decide from the measured rule at the first spmv()
+            self._dst = self._dst_unicast
         else:
             self.y_full = torch.empty(self.m_global, dtype=self.dtype, device=dev)
         self.y_local = self.y_full[self.row_begin:self.row_end]
@@ -146,6 +146,24 @@ class ShardedCsr5:
 
     def asCSR5(self) -> int:
         return self.h.asCSR5()
+
+    def _resolve_exchange(self):
+        """Scheme and store kind of the fused mode, fixed at the first spmv() (the matrix must be in CSR5
+        format).  Measured on 2 and 8 B200: rows stored by the SpMV kernels themselves win
+        when every tile stores a run of consecutive rows (no empty rows, short rows) and unicast peer stores
+        beat the multicast address for them; scattered row stores (dirty tiles, long rows) are better sent
+        by the coalesced push pass, through the multicast address once 4 or more GPUs take part."""
+        i = self.h.info()
+        if self.scheme == 0:
+            consecutive = not i.needs_zero_fill and (i.nnz // max(i.m, 1)) <= 64
+            self.scheme = 1 if consecutive else 2
+        self.h.set_option(self._H.OPT_EXCHANGE, self.scheme)
+        want = self._want_multicast
+        if want is None:
+            want = self.scheme == 2 and self.world >= 4
+        self.multicast = bool(want) and self._dst_multicast is not None
+        self._dst = self._dst_multicast if self.multicast else self._dst_unicast
+        self._resolved = True
 
     def spmv_local(self, alpha: float = 1.0) -> int:
         """Only this rank's rows (no exchange)."""
@@ -157,6 +175,8 @@ class ShardedCsr5:
         if self.world == 1:
             err = self.h.spmv(alpha, self.y_local)
         elif self._dst is not None:
+            if not self._resolved:
+                self._resolve_exchange()
             err = self.h.spmv_scatter(alpha, self.y_local, self._dst, len(self._dst), self.multicast)
             if not err:
                 self._symm.barrier(channel=0)  # all peers' stores have landed before anyone reads y

@@ -32,6 +32,8 @@ for name, A, sigma in cases:
         assert sh.asCSR5() == 0
         sh.y_full.fill_(float("nan")); torch.cuda.synchronize(); dist.barrier()
         log(name, mode, "spmv enqueue; multicast =", sh.multicast)
+        if sh._dst is not None:
+            sh._resolve_exchange()
         err = sh.h.spmv_scatter(1.0, sh.y_local, sh._dst, len(sh._dst), sh.multicast) if sh._dst is not None else sh.h.spmv(1.0, sh.y_local)
         log(name, mode, "enqueued err", err)
         torch.cuda.synchronize()

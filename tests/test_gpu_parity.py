@@ -332,3 +332,67 @@ def test_hot_column_table(torch_cuda, oracle):
     assert h.info().kernel_in_use == H.KERNEL_DIRECT
     assert np.array_equal(y, oracle.csr_spmv(B.m, B.row_ptr, B.col, val, x))
     h.free()
+
+
+def test_full_size_c4_laplacian_fp32(torch_cuda):
+    """BASELINE.json configs[3]: 27-pt Laplacian on 320^3 (879 M nnz, FP32, sigma 26 -> 2-packet descriptors,
+    byte offsets beyond 4 GiB).  Values are 26 / -1 and x is integer-valued, so every row sum is an integer
+    below 2^24: FP32 results must equal the FP64 prefix-sum segment sums bit for bit."""
+    torch = torch_cuda
+    rp, ci, v = M.device_laplacian27(320, dtype=torch.float32)
+    n = rp.numel() - 1
+    _, x = M.device_values(1, n, "int", torch.float32, "cuda")
+    _full_size_check(torch, rp, ci, v, x, torch.float32, kernels=(1, 2))
+
+
+def test_spmv_host_batch_pipeline(torch_cuda, oracle):
+    """csr5b200_spmv_host_batch: K independent SpMVs on host vectors, pipelined; every y_k must equal the
+    oracle's, including when buffers rotate (the double-buffered staging is reused every second vector)."""
+    torch = torch_cuda
+    name, A, sigma = CASES[4]
+    for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        val, _ = M.values(A.nnz, A.n, "int", dt)
+        h, _keep = _handle(torch, A, val, np.zeros(A.n, dt), sigma)
+        xs, ys, want = [], [], []
+        for k in range(7):
+            x = np.random.default_rng(k).integers(0, 10, A.n).astype(dt)
+            xs.append(torch.from_numpy(x).pin_memory())
+            ys.append(torch.full((A.m,), float("nan"), dtype=tdt).pin_memory())
+            want.append(oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x))
+        assert h.spmv_host_batch(1.0, xs, ys) == 0
+        for k in range(7):
+            assert np.array_equal(ys[k].numpy(), want[k]), (dt, k)
+        assert h.spmv_host_batch(2.0, xs[:1], ys[:1]) == 0
+        assert np.array_equal(ys[0].numpy(), 2 * want[0])
+        assert h.spmv_host_batch(1.0, [], []) == 0
+        h.free()
+
+
+def test_random_shapes_all_kernels(torch_cuda, oracle):
+    """40 seeded random row-length profiles x random sigma through every kernel variant."""
+    torch = torch_cuda
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        m, n = int(rng.integers(1, 3000)), int(rng.integers(1, 5000))
+        kind = trial % 4
+        if kind == 0:
+            cnt = rng.integers(0, 6, size=m)
+        elif kind == 1:
+            cnt = rng.integers(0, 70, size=m)
+        elif kind == 2:
+            cnt = rng.integers(0, 4, size=m)
+            cnt[rng.integers(0, m)] = rng.integers(200, 30000)
+        else:
+            cnt = (rng.random(m) < 0.1) * rng.integers(1, 30, size=m)
+        A = M.from_row_counts(cnt, n, seed=trial)
+        if A.nnz == 0:
+            continue
+        sigma = int(rng.choice([-1, 4, 5, 7, 12, 16, 17, 26, 31, 32]))
+        dt, tdt = ((np.float64, torch.float64), (np.float32, torch.float32))[trial % 2]
+        val, x = M.values(A.nnz, A.n, "int", dt, seed=trial)
+        y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+        for kernel in KERNELS:
+            h, _keep = _handle(torch, A, val, x, sigma, kernel)
+            y = _spmv(torch, h, A.m, tdt)
+            assert np.array_equal(y, y_ref), (trial, kernel, sigma, m, n)
+            h.free()

@@ -60,7 +60,7 @@ def test_reader_matches_reference_loader(name):
     assert (m, n) == (rm, rn)
     assert np.array_equal(rp, rrp) and np.array_equal(col, rcol) and np.array_equal(val, rval)
     if name != "skew":  # the reference does not expand skew-symmetric files; scipy does
-        want = scipy.io.mmread(io.StringIO(text)).toarray()
+        want = scipy.io.mmread(io.StringIO(text), spmatrix=False).toarray()
         got = sp.csr_matrix((val, col, rp), shape=(m, n)).toarray()   # duplicates are summed by both
         assert np.array_equal(got, want)
 

@@ -107,3 +107,44 @@ def test_tile_ptr_properties(oracle):
             b = min(t * 32 * s, A.nnz)
             r = rows[t]
             assert A.row_ptr[r] <= b and (r == A.m or A.row_ptr[r + 1] > b or r + 1 > A.m), name
+
+
+# ---- randomised shapes (hypothesis): oracle == scalar CSR == the reference's CSR5_avx2 -------------
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@st.composite
+def _random_csr(draw):
+    m = draw(st.integers(1, 400))
+    n = draw(st.integers(1, 600))
+    kind = draw(st.sampled_from(["short", "mixed", "hub", "sparse"]))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    if kind == "short":
+        cnt = rng.integers(0, 6, size=m)
+    elif kind == "mixed":
+        cnt = rng.integers(0, 70, size=m)
+    elif kind == "hub":
+        cnt = rng.integers(0, 4, size=m)
+        cnt[rng.integers(0, m)] = rng.integers(200, 4000)
+    else:
+        cnt = (rng.random(m) < 0.1) * rng.integers(1, 30, size=m)
+    sigma = draw(st.sampled_from([-1, 4, 5, 7, 12, 16, 17, 26, 31, 32]))
+    return M.from_row_counts(cnt, n, seed=seed + 1, name=f"{kind}_{m}x{n}"), sigma, seed
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(case=_random_csr())
+def test_oracle_random_shapes(oracle, case):
+    A, sigma, seed = case
+    if A.nnz == 0:
+        return
+    val, x = M.values(A.nnz, A.n, "int", np.float64, seed)
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    assert np.array_equal(oracle.csr5_spmv(A.m, A.n, A.row_ptr, A.col, val, x, sigma), y_ref)
+    if oracle.ref_available():
+        assert np.array_equal(oracle.ref_avx2_spmv(A.m, A.n, A.row_ptr, A.col, val, x), y_ref)
+    val, x = M.values(A.nnz, A.n, "real", np.float64, seed)
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    assert np.allclose(oracle.csr5_spmv(A.m, A.n, A.row_ptr, A.col, val, x, sigma), y_ref, rtol=1e-12, atol=0)

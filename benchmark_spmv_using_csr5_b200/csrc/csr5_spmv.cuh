@@ -3,15 +3,17 @@
 // One warp owns one omega x sigma tile (omega = 32), as in the reference
 // (csr5_spmv_cuda.h:275-311), but the data path and the write-back are re-designed:
 //
-//  * TMA-staged kernel (default): persistent CTAs; every warp runs its own S-deep ring of
-//    shared-memory slots that it fills with 1-D bulk TMA copies (cp.async.bulk -> UBLKCP) of the
-//    tile's val slab, col slab and descriptor words, completing on one mbarrier per slot.  The warp
-//    that consumes a slot is the warp that refills it, so there is no producer/consumer coupling
-//    between warps and no empty-barrier: S - 1 tiles (6 KB each at sigma 16 / FP64) are always in
-//    flight per warp while one is being reduced out of conflict-free shared memory.  x is gathered
-//    with LDG (read-only path); there is no reuse to stage.
-//  * direct-load kernel: one warp per tile, register-staged streaming loads (ld.global.cs), for
-//    arrays that are not 16-byte aligned and as the A/B comparison for the ncu captures.
+//  * direct-load kernel (default): one warp per tile, register-staged streaming loads (ld.global.cs) in
+//    chunks sized by measurement (ChunkOf), LDG gathers of x.  On B200 it streams the banded 10M matrix at
+//    1.01 of the measured HBM copy bandwidth (profiles/r01_ncu_full_c2_direct.md).
+//  * TMA-staged kernel (CSR5B200_OPT_KERNEL = 2): persistent CTAs; every warp runs its own S-deep ring of
+//    shared-memory slots that it fills with 1-D bulk TMA copies (cp.async.bulk -> UBLKCP) of the tile's val
+//    slab, col slab and descriptor words, completing on one mbarrier per slot.  The warp that consumes a
+//    slot is the warp that refills it, so there is no producer/consumer coupling between warps and no
+//    empty-barrier.  Measured slower than the direct kernel (few fat warps expose the x-gather latency);
+//    kept as the A/B evidence (profiles/r01_ncu_full_c2_tma.md).
+//  * hot-column kernel (CSR5B200_OPT_HOT_COLUMNS): direct loads + the most referenced x entries staged in
+//    shared memory by bulk TMA, for power-law matrices.
 //
 //  * In-lane reduction: the sigma bit flags of a lane are unpacked ONCE into a 32-bit mask, so the
 //    fully unrolled loop tests compile-time bits instead of shifting a descriptor per element
@@ -28,6 +30,8 @@
 //    rows before the tail (then y is memset first).  The reference's third launch, the tail
 //    kernel (csr5_spmv_cuda.h:384-419), is folded into the first: the leading warps of the grid
 //    reduce the rows of the last, partial tile CSR-vector style.
+//  * Sharded (multi-GPU) mode: the same kernels with every y store replicated to all GPUs (MULTI), or a
+//    coalesced push pass after the SpMV; see csr5b200_spmv_scatter in include/csr5_b200.h.
 #ifndef CSR5_SPMV_CUH
 #define CSR5_SPMV_CUH
 

@@ -77,18 +77,33 @@ class ClockSampler:
         0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period_s: float = 0.004):
+    def __init__(self, index: int, period_s: float = 0.004, uuid: str | None = None):
+        """index: CUDA device ordinal of this process; uuid: that device's UUID.  NVML numbers the
+        physical GPUs and ignores CUDA_VISIBLE_DEVICES, so the device is looked up by UUID first."""
         self.index, self.period = index, period_s
         self.samples = []  # (t, sm_mhz, reasons bitmask)
         self.max_mhz = None
         self._stop = threading.Event()
         self._thr = None
         self._nvml = None
+        self._smi_id = str(index)
+        cvd = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [t.strip() for t in cvd.split(",") if t.strip()]
+        if uuid:
+            self._smi_id = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        elif index < len(ids):
+            self._smi_id = ids[index]
         try:
             import pynvml
             pynvml.nvmlInit()
             self._nvml = pynvml
-            self._dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            try:
+                if not self._smi_id.startswith("GPU-"):
+                    raise ValueError("no uuid")
+                self._dev = pynvml.nvmlDeviceGetHandleByUUID(self._smi_id)
+            except Exception:
+                phys = int(self._smi_id) if self._smi_id.isdigit() else index
+                self._dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._dev, pynvml.NVML_CLOCK_SM))
         except Exception as e:  # pragma: no cover
             log(f"[bench] NVML unavailable ({e}); falling back to nvidia-smi")
@@ -103,7 +118,7 @@ class ClockSampler:
                 rs = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._dev))
             return mhz, rs
         out = subprocess.run(
-            ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+            ["nvidia-smi", "-i", self._smi_id, "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout.strip()
         a = [t.strip() for t in out.split(",")]
         self.max_mhz = float(a[1])
@@ -389,7 +404,11 @@ def main():
         dist.all_gather(allcs, cs)
         assert all(torch.allclose(c, allcs[0], rtol=1e-12) for c in allcs), "ranks disagree on the gathered y"
 
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, uuid=dev_uuid)
     sampler.start()
     windows = []
 

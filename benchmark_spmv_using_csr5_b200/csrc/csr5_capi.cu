@@ -70,9 +70,9 @@ void release_csr5_arrays(csr5b200_handle_t h)
     pl.dev_flags = nullptr;
 }
 
-// anonymouslib_cuda.h:294-318 -- r / s / t / u = 4 / 32 / 256 / 6 on k = nnz / m
 constexpr size_t MAX_TIMED_SPMV = 4096;
 
+// anonymouslib_cuda.h:294-318 -- r / s / t / u = 4 / 32 / 256 / 6 on k = nnz / m
 int auto_sigma(int m, int nnz)
 {
     const int k = m > 0 ? nnz / m : 0;
@@ -318,7 +318,11 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
     scan_scratch = nullptr;
     {
         const int err = build_hot_table(h);
-        if (err) { release_csr5_arrays(h); return err; }
+        if (err) {  // leave the caller's arrays as they were handed in: undo the transpose
+            if (launch_transpose(pl, false, h->stream) == cudaSuccess) cudaStreamSynchronize(h->stream);
+            release_csr5_arrays(h);
+            return err;
+        }
     }
 #undef CUF
     h->format = CSR5B200_FORMAT_CSR5;

@@ -291,7 +291,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto (= direct-load), 1 direct-load, 2 TMA-staged")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto (= direct-load), 1 direct-load, 2 TMA-staged, 4 TMA-staged + x prefetch")
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
@@ -550,7 +550,8 @@ def main():
     k_ms = float(kt.mean()) if kt.size else ms_step
     achieved = b_alg / (k_ms * 1e6)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": {1: "spmv_direct_kernel", 2: "spmv_tma_kernel", 3: "spmv_hot_kernel"}.get(info.kernel_in_use, "?"),
+                "traffic": None, "kernel": {1: "spmv_direct_kernel", 2: "spmv_tma_kernel", 3: "spmv_hot_kernel",
+                                                   4: "spmv_tma_kernel<prefetch>"}.get(info.kernel_in_use, "?"),
                 "kernel_ms_avg": k_ms, "kernel_ms_min": float(kt.min()) if kt.size else None,
                 "kernel_launches_timed": int(kt.size), "algorithmic_bytes_per_launch": b_alg,
                 "bytes_per_nnz": b_alg / nnz, "peak_source": peak_src,

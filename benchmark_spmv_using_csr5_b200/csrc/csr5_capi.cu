@@ -217,7 +217,7 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
     if (!h) return CSR5B200_INVALID_ARGUMENT;
     switch (option) {
         case CSR5B200_OPT_KERNEL:
-            if (value < 0 || value > 2) return CSR5B200_INVALID_ARGUMENT;
+            if (value < 0 || value > 4 || value == 3) return CSR5B200_INVALID_ARGUMENT;
             h->tune.kernel = value;
             break;
         case CSR5B200_OPT_IGNORE_ALPHA: h->ignore_alpha = value != 0; break;

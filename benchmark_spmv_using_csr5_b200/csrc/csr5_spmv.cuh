@@ -10,8 +10,9 @@
 //    shared-memory slots that it fills with 1-D bulk TMA copies (cp.async.bulk -> UBLKCP) of the tile's val
 //    slab, col slab and descriptor words, completing on one mbarrier per slot.  The warp that consumes a
 //    slot is the warp that refills it, so there is no producer/consumer coupling between warps and no
-//    empty-barrier.  Measured slower than the direct kernel (few fat warps expose the x-gather latency);
-//    kept as the A/B evidence (profiles/r01_ncu_full_c2_tma.md).
+//    empty-barrier.  Measured slower than the direct kernel (few fat warps expose the x-gather latency;
+//    profiles/r01_ncu_full_c2_tma.md); with the x gathers prefetched one tile ahead (CSR5B200_OPT_KERNEL = 4)
+//    it reaches 0.97-1.00 of the roofline on the banded FP64 stream (profiles/r01_tma_prefetch.txt).
 //  * hot-column kernel (CSR5B200_OPT_HOT_COLUMNS): direct loads + the most referenced x entries staged in
 //    shared memory by bulk TMA, for power-law matrices.
 //
@@ -122,6 +123,7 @@ __device__ __forceinline__ uint32_t unpack_flags(uint32_t w0, uint32_t w1, int b
 template <typename VT>
 struct GlobalTile {  // direct-load kernel: streaming loads, evict-first
     static constexpr bool kStageInRegisters = true;  // issue all val/col loads of a chunk up front
+    static constexpr bool kHasX = false;
     const VT *val;
     const int *col;
     const uint32_t *desc;
@@ -136,6 +138,7 @@ struct GlobalTile {  // direct-load kernel: streaming loads, evict-first
 template <typename VT>
 struct HotTile {
     static constexpr bool kStageInRegisters = true;
+    static constexpr bool kHasX = false;
     const VT *val;
     const int *col;
     const uint32_t *desc;
@@ -152,9 +155,26 @@ struct HotTile {
 template <typename VT>
 struct SharedTile {  // TMA-staged kernel: conflict-free LDS (consecutive lanes, consecutive words)
     static constexpr bool kStageInRegisters = false;  // val/col are one LDS away: only x needs registers
+    static constexpr bool kHasX = false;
     const VT *val;
     const int *col;
     const uint32_t *desc;
+    __device__ __forceinline__ VT v(int i, int lane) const { return val[i * OMEGA + lane]; }
+    __device__ __forceinline__ int c(int i, int lane) const { return col[i * OMEGA + lane]; }
+    __device__ __forceinline__ uint32_t d(int k, int lane) const { return desc[k * OMEGA + lane]; }
+    __device__ __forceinline__ VT xv(const VT *__restrict__ x, int c) const { return __ldg(x + c); }
+};
+
+// TMA-staged kernel with x prefetch: as SharedTile, but the x values of the tile were gathered one
+// tile ahead into registers (xr[i] = x[col(i, lane)]).
+template <typename VT>
+struct PrefetchedTile {
+    static constexpr bool kStageInRegisters = false;
+    static constexpr bool kHasX = true;
+    const VT *val;
+    const int *col;
+    const uint32_t *desc;
+    const VT *xr;
     __device__ __forceinline__ VT v(int i, int lane) const { return val[i * OMEGA + lane]; }
     __device__ __forceinline__ int c(int i, int lane) const { return col[i * OMEGA + lane]; }
     __device__ __forceinline__ uint32_t d(int k, int lane) const { return desc[k * OMEGA + lane]; }
@@ -197,7 +217,10 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
             }
 #pragma unroll
             for (int k = 0; k < CH; k++)
-                if (c0 + k < SIGMA) xv[k] = tile.xv(x, Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane));
+                if (c0 + k < SIGMA) {
+                    if constexpr (Tile::kHasX) xv[k] = tile.xr[c0 + k];
+                    else xv[k] = tile.xv(x, Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane));
+                }
 #pragma unroll
             for (int k = 0; k < CH; k++)
                 if (c0 + k < SIGMA)
@@ -236,7 +259,10 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
         }
 #pragma unroll
         for (int k = 0; k < CH; k++)
-            if (c0 + k < SIGMA) xv[k] = tile.xv(x, Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane));
+            if (c0 + k < SIGMA) {
+                if constexpr (Tile::kHasX) xv[k] = tile.xr[c0 + k];
+                else xv[k] = tile.xv(x, Tile::kStageInRegisters ? c[k] : tile.c(c0 + k, lane));
+            }
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const int i = c0 + k;
@@ -383,7 +409,10 @@ struct TmaSlot {
 };
 
 // grid = persistent CTAs; warp gw handles tiles gw, gw + GW, gw + 2 GW, ... (GW = warps in the grid)
-template <typename VT, int SIGMA>
+// PREFETCH (CSR5B200_OPT_KERNEL = 4): the x gathers of the NEXT tile are issued (from its col slab, already
+// landed in the ring) before the current tile is reduced, so a warp's gather latency overlaps its own
+// arithmetic instead of being exposed once per tile -- the cause of the plain ring's 87 %.
+template <typename VT, int SIGMA, bool PREFETCH>
 __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const SpmvArgs<VT> a, const int stages)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -432,29 +461,74 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
 
     int s = 0;
     uint32_t parity = 0;
-    for (long long t = gw; t < ntiles; t += GW) {
-        // tile_ptr words of the next tile are fetched one iteration ahead
-        const long long tn = t + GW;
-        uint32_t nstart = 0, nstop = 0;
-        if (tn < ntiles) { nstart = __ldg(a.tile_ptr + tn); nstop = __ldg(a.tile_ptr + tn + 1); }
+    if constexpr (!PREFETCH) {
+        for (long long t = gw; t < ntiles; t += GW) {
+            // tile_ptr words of the next tile are fetched one iteration ahead
+            const long long tn = t + GW;
+            uint32_t nstart = 0, nstop = 0;
+            if (tn < ntiles) { nstart = __ldg(a.tile_ptr + tn); nstop = __ldg(a.tile_ptr + tn + 1); }
 
-        mbar_wait(smem_u32(bars + s), parity);
-        const unsigned char *slot = my_slots + (size_t)s * Slot::BYTES;
-        SharedTile<VT> tile{reinterpret_cast<const VT *>(slot),
-                            reinterpret_cast<const int *>(slot + Slot::VAL_BYTES),
-                            reinterpret_cast<const uint32_t *>(slot + Slot::VAL_BYTES + Slot::COL_BYTES)};
-        process_tile<VT, SIGMA, false>(a, tile, (int)t, lane, raw_start, raw_stop);
+            mbar_wait(smem_u32(bars + s), parity);
+            const unsigned char *slot = my_slots + (size_t)s * Slot::BYTES;
+            SharedTile<VT> tile{reinterpret_cast<const VT *>(slot),
+                                reinterpret_cast<const int *>(slot + Slot::VAL_BYTES),
+                                reinterpret_cast<const uint32_t *>(slot + Slot::VAL_BYTES + Slot::COL_BYTES)};
+            process_tile<VT, SIGMA, false>(a, tile, (int)t, lane, raw_start, raw_stop);
 
-        // this warp is done reading slot s: refill it with the tile `stages` iterations ahead
-        __syncwarp();
-        const long long tf = t + (long long)stages * GW;
-        if (lane == 0 && tf < ntiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(tf, s);
+            // this warp is done reading slot s: refill it with the tile `stages` iterations ahead
+            __syncwarp();
+            const long long tf = t + (long long)stages * GW;
+            if (lane == 0 && tf < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(tf, s);
+            }
+            raw_start = nstart;
+            raw_stop = nstop;
+            if (++s == stages) { s = 0; parity ^= 1u; }
         }
-        raw_start = nstart;
-        raw_stop = nstop;
-        if (++s == stages) { s = 0; parity ^= 1u; }
+    } else {
+        VT xc[SIGMA], xn[SIGMA];
+#pragma unroll
+        for (int i = 0; i < SIGMA; i++) { xc[i] = (VT)0; xn[i] = (VT)0; }
+        if (gw < ntiles) {  // x of this warp's first tile
+            mbar_wait(smem_u32(bars), 0);
+            const int *col0 = reinterpret_cast<const int *>(my_slots + Slot::VAL_BYTES);
+#pragma unroll
+            for (int i = 0; i < SIGMA; i++) xc[i] = __ldg(a.x + col0[i * OMEGA + lane]);
+        }
+        for (long long t = gw; t < ntiles; t += GW) {
+            const long long tn = t + GW;
+            int sn = s + 1;
+            uint32_t pn = parity;
+            if (sn == stages) { sn = 0; pn ^= 1u; }
+            uint32_t nstart = 0, nstop = 0;
+            if (tn < ntiles) {
+                nstart = __ldg(a.tile_ptr + tn);
+                nstop = __ldg(a.tile_ptr + tn + 1);
+                mbar_wait(smem_u32(bars + sn), pn);  // issued one full tile ago: normally landed
+                const int *coln = reinterpret_cast<const int *>(my_slots + (size_t)sn * Slot::BYTES + Slot::VAL_BYTES);
+#pragma unroll
+                for (int i = 0; i < SIGMA; i++) xn[i] = __ldg(a.x + coln[i * OMEGA + lane]);
+            }
+            const unsigned char *slot = my_slots + (size_t)s * Slot::BYTES;
+            PrefetchedTile<VT> tile{reinterpret_cast<const VT *>(slot),
+                                    reinterpret_cast<const int *>(slot + Slot::VAL_BYTES),
+                                    reinterpret_cast<const uint32_t *>(slot + Slot::VAL_BYTES + Slot::COL_BYTES), xc};
+            process_tile<VT, SIGMA, false>(a, tile, (int)t, lane, raw_start, raw_stop);
+
+            __syncwarp();
+            const long long tf = t + (long long)stages * GW;
+            if (lane == 0 && tf < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(tf, s);
+            }
+#pragma unroll
+            for (int i = 0; i < SIGMA; i++) xc[i] = xn[i];
+            raw_start = nstart;
+            raw_stop = nstop;
+            s = sn;
+            parity = pn;
+        }
     }
 }
 
@@ -648,7 +722,7 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
     // auto = direct-load: on B200 it streams C2 at 98 % of the measured HBM copy bandwidth vs 87 % for
     // the TMA-staged ring (profiles/r01_*; the ring's few, fat warps expose the x-gather latency).
     if (kernel == 0) kernel = 1;
-    if (kernel == 2 && !tma_ok) kernel = 1;
+    if ((kernel == 2 || kernel == 4) && !tma_ok) kernel = 1;
     if (ntiles <= 0 || multi) kernel = 1;  // the multi-destination (sharded) variant exists for the direct kernel
     *used = kernel;
 
@@ -697,19 +771,19 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
     if (warps < 1) warps = 1;
     while (warps > 1 && (size_t)warps * stages * per_slot > (size_t)226 * 1024) warps--;
     const size_t smem = (size_t)warps * stages * (Slot::BYTES + 8);
-    static bool attr_set = false;  // per (VT, SIGMA) instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(spmv_tma_kernel<VT, SIGMA>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    if (stages < 2 && kernel == 4) kernel = 2;  // the prefetch needs a second slot to read ahead from
+    *used = kernel;
     long long grid = (long long)tn.num_sms * ctas_per_sm;
     const long long need = (ntiles + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    spmv_tma_kernel<VT, SIGMA><<<(unsigned)grid, warps * 32, smem, stream>>>(a, stages);
-    return cudaGetLastError();
+    auto run = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)grid, warps * 32, smem, stream>>>(a, stages);
+        return cudaGetLastError();
+    };
+    return kernel == 4 ? run(spmv_tma_kernel<VT, SIGMA, true>) : run(spmv_tma_kernel<VT, SIGMA, false>);
 }
 
 template <typename VT>

@@ -49,7 +49,7 @@ OPT_HOT_COLUMNS = 9
 OPT_HOT_THREADS = 10
 OPT_EXCHANGE = 11
 EXCHANGE_AUTO, EXCHANGE_FUSED, EXCHANGE_PUSH = 0, 1, 2
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_HOT = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_HOT, KERNEL_TMA_PREFETCH = 0, 1, 2, 3, 4
 
 
 def _ptr(t):

@@ -115,7 +115,8 @@ CSR5B200_API int csr5b200_free(csr5b200_handle_t h);
 /* Stream all later work of this handle is issued on (a cudaStream_t; NULL = legacy default). */
 CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
 
-#define CSR5B200_OPT_KERNEL        1  /* 0 auto (default; = the faster one on B200: direct-load), 1 direct-load kernel, 2 TMA-staged kernel */
+#define CSR5B200_OPT_KERNEL        1  /* 0 auto (default; = the faster one on B200: direct-load), 1 direct-load kernel, 2 TMA-staged kernel,
+                                         4 TMA-staged kernel with the x gathers prefetched one tile ahead */
 #define CSR5B200_OPT_IGNORE_ALPHA  2  /* 1 = reference bug-compat: alpha treated as 1 */
 #define CSR5B200_OPT_TMA_STAGES    3  /* smem ring depth of the TMA-staged kernel (0 = default) */
 #define CSR5B200_OPT_TMA_WARPS     4  /* consumer warps per CTA of the TMA-staged kernel (0 = default) */
@@ -146,7 +147,7 @@ typedef struct csr5b200_info {
     int num_offsets;       /* _num_offsets */
     int tail_partition_start; /* _tail_partition_start */
     int needs_zero_fill;   /* 1 if some row before the tail is empty (y is memset inside spmv) */
-    int kernel_in_use;     /* 1 direct-load, 2 TMA-staged, 3 hot-column (direct-load + x table in shared memory) */
+    int kernel_in_use;     /* 1 direct-load, 2 TMA-staged, 3 hot-column (direct-load + x table in shared memory), 4 TMA-staged + x prefetch */
     const uint32_t *partition_pointer;           /* (p + 1) */
     const uint32_t *partition_descriptor;        /* p * 32 * num_packet */
     const int32_t  *partition_descriptor_offset_pointer; /* (p + 1) */

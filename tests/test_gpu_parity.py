@@ -30,9 +30,12 @@ def _upload(torch, A, val, x):
 
 
 # kernel ids: 1 direct-load, 2 TMA-staged (both with the hot-column table off), 3 hot-column kernel with
-# the automatic table, 4 hot-column kernel with a tiny forced table (tagged and untagged columns mixed)
-KERNELS = [1, 2, 3, 4]
-KERNEL_IDS = ["direct", "tma", "hot_auto", "hot_k48"]
+# the automatic table, 4 hot-column kernel with a tiny forced table (tagged and untagged columns mixed),
+# 5 TMA-staged with the x gathers prefetched one tile ahead (CSR5B200_OPT_KERNEL = 4)
+KERNELS = [1, 2, 3, 4, 5]
+KERNEL_IDS = ["direct", "tma", "hot_auto", "hot_k48", "tma_prefetch"]
+_OPT_KERNEL = {0: 0, 1: 1, 2: 2, 3: 0, 4: 0, 5: 4}
+_OPT_HOT = {0: -1, 1: 0, 2: 0, 3: -1, 4: 48, 5: 0}
 
 
 def _handle(torch, A, val, x, sigma, kernel=0):
@@ -43,8 +46,8 @@ def _handle(torch, A, val, x, sigma, kernel=0):
     assert h.inputCSR(A.nnz, rp, ci, v) == 0
     assert h.setX(xd) == 0
     h.setSigma(sigma)
-    assert h.set_option(H.OPT_KERNEL, kernel if kernel in (0, 1, 2) else 0) == 0
-    assert h.set_option(H.OPT_HOT_COLUMNS, {0: -1, 1: 0, 2: 0, 3: -1, 4: 48}[kernel]) == 0
+    assert h.set_option(H.OPT_KERNEL, _OPT_KERNEL[kernel]) == 0
+    assert h.set_option(H.OPT_HOT_COLUMNS, _OPT_HOT[kernel]) == 0
     assert h.warmup() == 0
     assert h.asCSR5() == 0
     return h, (rp, ci, v, xd)
@@ -249,7 +252,7 @@ def _segment_sums_exact(torch, rp, ci, v, x):
     return cs[rp[1:].long()] - cs[rp[:-1].long()]
 
 
-def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2, 3)):
+def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2, 3, 5)):
     from benchmark_spmv_using_csr5_b200 import handle as H
     m, n, nnz = rp.numel() - 1, x.numel(), ci.numel()
     y_ref = _segment_sums_exact(torch, rp, ci, v, x).to(dtype)
@@ -259,8 +262,8 @@ def _full_size_check(torch, rp, ci, v, x, dtype, kernels=(1, 2, 3)):
         assert h.inputCSR(nnz, rp, ci, v) == 0
         h.setX(x)
         h.setSigma(-1)
-        h.set_option(H.OPT_KERNEL, kernel if kernel < 3 else 0)
-        h.set_option(H.OPT_HOT_COLUMNS, -1 if kernel == 3 else 0)
+        h.set_option(H.OPT_KERNEL, _OPT_KERNEL[kernel])
+        h.set_option(H.OPT_HOT_COLUMNS, _OPT_HOT[kernel])
         assert h.asCSR5() == 0
         y = torch.full((m,), float("nan"), device="cuda", dtype=dtype)
         assert h.spmv(1.0, y) == 0
@@ -342,7 +345,7 @@ def test_full_size_c4_laplacian_fp32(torch_cuda):
     rp, ci, v = M.device_laplacian27(320, dtype=torch.float32)
     n = rp.numel() - 1
     _, x = M.device_values(1, n, "int", torch.float32, "cuda")
-    _full_size_check(torch, rp, ci, v, x, torch.float32, kernels=(1, 2))
+    _full_size_check(torch, rp, ci, v, x, torch.float32, kernels=(1, 2, 5))
 
 
 def test_spmv_host_batch_pipeline(torch_cuda, oracle):

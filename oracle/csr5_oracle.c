@@ -12,7 +12,7 @@
  *        oracle/_ref/libref_avx2.so (y, bit-exact on the reference's integer-valued input
  *        distribution, <= 1e-12 rel on real-valued inputs), and
  *   (ii) golden vectors produced by the reference's own CSR5_cuda backend (compat-patched build,
- *        oracle/build_ref.sh) run on a B200 -- tests/golden/refcuda_*.npz -- covering tile_ptr,
+ *        oracle/build_ref_cuda.sh) run on a B200 -- tests/golden/refcuda_*.npz -- covering tile_ptr,
  *        tile_desc, the empty-row offset table, the transposed col/val arrays and y.
  *
  * Every function cites the reference file:line (relative to /root/reference/CSR5_cuda) it follows.

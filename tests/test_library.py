@@ -78,3 +78,52 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, re.M), f
                 assert "csr5_oracle" not in txt and "libref_" not in txt, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/csr5_b200.h is a C ABI: a C99 translation unit includes it, links against the library and
+    calls entry points that need no GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "csr5_b200.h"\n'
+                   'int main(void) { csr5b200_handle_t h = 0; csr5b200_info info;\n'
+                   '  if (csr5b200_create(3, 4, 8, &h)) return 1;\n'
+                   '  if (csr5b200_get_info(h, &info) || info.m != 3 || info.n != 4) return 2;\n'
+                   '  if (csr5b200_spmv(h, 1.0, (void *)16) != CSR5B200_UNKNOWN_FORMAT) return 3;\n'
+                   '  puts(csr5b200_version()); puts(csr5b200_error_string(CSR5B200_UNSUPPORTED_CSR_SPMV));\n'
+                   '  return csr5b200_free(h); }\n')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lcsr5_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "csr5-b200" in r.stdout and "asCSR5" in r.stdout, r.stdout + r.stderr
+
+
+def test_cpp_shim_compiles_standalone(tmp_path):
+    """include/anonymouslib_cuda.h: the reference's call sequence (main.cu:59-108) compiles against the shim
+    for both value types (compile only; the run is tests/test_gpu_dropin.py)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc")
+    if not nvcc:
+        pytest.skip("nvcc not found")
+    src = tmp_path / "t.cu"
+    src.write_text('#include "anonymouslib_cuda.h"\n'
+                   'template <typename VT> int run(int m, int n, int nnz, int *rp, int *ci, VT *v, VT *x, VT *y) {\n'
+                   '  anonymouslibHandle<int, unsigned int, VT> A(m, n);\n'
+                   '  int err = A.inputCSR(nnz, rp, ci, v); err = A.setX(x);\n'
+                   '  A.setSigma(ANONYMOUSLIB_AUTO_TUNED_SIGMA); A.warmup();\n'
+                   '  anonymouslib_timer t; t.start(); err = A.asCSR5(); (void)t.stop();\n'
+                   '  err = A.spmv((VT)1.0, y); A.destroy();\n'
+                   '  double gb = getB<int, VT>(m, nnz), gf = getFLOP<int>(nnz); (void)gb; (void)gf;\n'
+                   '  return err == ANONYMOUSLIB_SUCCESS ? 0 : err; }\n'
+                   'template int run<double>(int, int, int, int *, int *, double *, double *, double *);\n'
+                   'template int run<float>(int, int, int, int *, int *, float *, float *, float *);\n')
+    r = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I",
+                        os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -12,6 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcsr5_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "csr5_b200.h")
+HEADER_PATHS = [HEADER_PATH, os.path.join(os.path.dirname(_HERE), "include", "csr5_b200_sharded.h")]
 
 
 class Csr5LibraryMissing(RuntimeError):
@@ -31,6 +32,22 @@ class Csr5Info(C.Structure):
         ("partition_descriptor_offset", C.c_void_p), ("calibrator", C.c_void_p),
         ("last_cuda_error", C.c_int), ("launches_per_spmv", C.c_int),
         ("hot_columns", C.c_int), ("hot_coverage", C.c_double),
+        ("convert_phase_ms", C.c_float * 8), ("convert_host_ms", C.c_double), ("convert_alloc_ms", C.c_double),
+        ("exchange_transport", C.c_int), ("exchange_chunks", C.c_int),
+    ]
+
+
+MAX_SCATTER = 8  # CSR5B200_MAX_SCATTER
+
+
+class Csr5Exchange(C.Structure):
+    """struct csr5b200_exchange of include/csr5_b200.h"""
+    _fields_ = [
+        ("rank", C.c_int), ("world", C.c_int),
+        ("y_full", C.c_void_p * MAX_SCATTER), ("y_multicast", C.c_void_p),
+        ("flags", C.c_void_p * MAX_SCATTER), ("row_begin", C.c_longlong),
+        ("chunks", C.c_int), ("transport", C.c_int), ("entry_barrier", C.c_int),
+        ("push_ctas", C.c_int), ("timeout_ms", C.c_int),
     ]
 
 
@@ -43,6 +60,9 @@ SIGNATURES = {
     "csr5b200_as_csr5": (C.c_int, [C.c_void_p]),
     "csr5b200_set_x": (C.c_int, [C.c_void_p, C.c_void_p]),
     "csr5b200_spmv": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "csr5b200_spmv_axpby": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
+    "csr5b200_spmv_allgather": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.POINTER(Csr5Exchange)]),
+    "csr5b200_exchange_status": (C.c_int, [C.c_void_p]),
     "csr5b200_spmv_scatter": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
                                          C.c_int]),
     "csr5b200_destroy": (C.c_int, [C.c_void_p]),
@@ -52,6 +72,7 @@ SIGNATURES = {
     "csr5b200_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "csr5b200_get_info": (C.c_int, [C.c_void_p, C.POINTER(Csr5Info)]),
     "csr5b200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+    "csr5b200_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "csr5b200_copy_meta_to_host": (C.c_int, [C.c_void_p] * 6),
     "csr5b200_spmv_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "csr5b200_spmv_host_batch": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_void_p),
@@ -59,6 +80,23 @@ SIGNATURES = {
     "csr5b200_call_anonymouslib": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                               C.c_int, C.c_int]),
+    # include/csr5_b200_sharded.h
+    "csr5b200_sharded_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "csr5b200_sharded_input_csr_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p]),
+    "csr5b200_sharded_set_sigma": (C.c_int, [C.c_void_p, C.c_int]),
+    "csr5b200_sharded_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "csr5b200_sharded_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "csr5b200_sharded_set_x_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "csr5b200_sharded_as_csr5": (C.c_int, [C.c_void_p]),
+    "csr5b200_sharded_spmv": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "csr5b200_sharded_iterate": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "csr5b200_sharded_synchronize": (C.c_int, [C.c_void_p]),
+    "csr5b200_sharded_get_y": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "csr5b200_sharded_copy_y_to_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "csr5b200_sharded_get_bounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+    "csr5b200_sharded_get_handle": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "csr5b200_sharded_destroy": (C.c_int, [C.c_void_p]),
     "csr5b200_version": (C.c_char_p, []),
     "csr5b200_error_string": (C.c_char_p, [C.c_int]),
 }

@@ -2,44 +2,27 @@
 // (include/csr5_b200.h).  Mirrors anonymouslibHandle<int, unsigned int, VT>
 // (CSR5_cuda/anonymouslib_cuda.h:11-318): CSR arrays are borrowed, the five CSR5 arrays are owned,
 // col/val are permuted in place between asCSR5() and asCSR().
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
 
-#include "csr5_internal.h"
+#include "csr5_handle.h"
 
 using namespace csr5;
 
-struct csr5b200_handle_s {
-    Plan pl;
-    SpmvTuning tune;
-    int format = -1;          // the reference leaves _format unset until inputCSR
-    cudaStream_t stream = 0;  // legacy default stream, like the reference
-    int ignore_alpha = 0;
-    int last_cuda_error = 0;
-    int kernel_in_use = 0;
-    int launches_per_spmv = 0;
-    void *x_stage = nullptr;  // device staging for spmv_host
-    void *y_stage = nullptr;
-    // spmv_host_batch pipeline: double-buffered staging, copy streams, events
-    void *xb[2] = {nullptr, nullptr}, *yb[2] = {nullptr, nullptr};
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    // sharded mode (spmv_scatter)
-    ShardCtx shard;
-    cudaEvent_t e_in[2] = {nullptr, nullptr}, e_comp[2] = {nullptr, nullptr}, e_out[2] = {nullptr, nullptr};
-    int kernel_timing = 0;
-    std::vector<cudaEvent_t> ev;  // begin/end pairs of the timed main kernels
-    size_t ev_used = 0;           // events recorded since the last get_kernel_times()
-};
-
-namespace {
-
-int cuda_fail(csr5b200_handle_t h, cudaError_t e)
+namespace csr5 {
+int handle_cuda_fail(csr5b200_handle_t h, cudaError_t e)
 {
     if (h) h->last_cuda_error = (int)e;
     return CSR5B200_CUDA_ERROR;
 }
+}  // namespace csr5
+
+namespace {
+
+int cuda_fail(csr5b200_handle_t h, cudaError_t e) { return handle_cuda_fail(h, e); }
 
 #define CU(h, call)                                        \
     do {                                                   \
@@ -47,15 +30,10 @@ int cuda_fail(csr5b200_handle_t h, cudaError_t e)
         if (e__ != cudaSuccess) return cuda_fail(h, e__);  \
     } while (0)
 
+// The CSR5 arrays go back to the handle's buffer pool (the memory is kept for the next asCSR5()).
 void release_csr5_arrays(csr5b200_handle_t h)
 {
     Plan &pl = h->pl;
-    cudaFree(pl.tile_ptr);
-    cudaFree(pl.desc);
-    cudaFree(pl.desc_off_ptr);
-    cudaFree(pl.desc_off);
-    cudaFree(pl.calibrator);
-    cudaFree(pl.dev_flags);
     cudaFree(pl.hot_col);
     cudaFree(pl.hot_x);
     pl.hot_col = nullptr;
@@ -68,6 +46,38 @@ void release_csr5_arrays(csr5b200_handle_t h)
     pl.desc_off = nullptr;
     pl.calibrator = nullptr;
     pl.dev_flags = nullptr;
+    h->ex.chunks = 0;   // row-block boundaries of the exchange belong to the released tile_ptr
+    h->ex.chunk_tile.clear();
+    h->ex.chunk_row.clear();
+}
+
+void free_pool(csr5b200_handle_t h)
+{
+    for (int k = 0; k < csr5b200_handle_s::POOL_SLOTS; k++) {
+        cudaFree(h->pool[k]);
+        h->pool[k] = nullptr;
+        h->pool_cap[k] = 0;
+    }
+    for (auto &e : h->ev_conv) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
+}
+
+// A buffer of at least `bytes` from slot `slot` of the pool (grown when too small).
+cudaError_t pool_get(csr5b200_handle_t h, int slot, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 16;
+    if (h->pool_cap[slot] < bytes) {
+        cudaFree(h->pool[slot]);
+        h->pool[slot] = nullptr;
+        h->pool_cap[slot] = 0;
+        const cudaError_t e = cudaMalloc(&h->pool[slot], bytes);
+        if (e != cudaSuccess) return e;
+        h->pool_cap[slot] = bytes;
+    }
+    *out = h->pool[slot];
+    return cudaSuccess;
 }
 
 constexpr size_t MAX_TIMED_SPMV = 4096;
@@ -76,6 +86,18 @@ constexpr size_t MAX_TIMED_SPMV = 4096;
 int auto_sigma(int m, int nnz)
 {
     const int k = m > 0 ? nnz / m : 0;
+    if (k <= 4) return 4;
+    if (k <= 32) return k;
+    if (k <= 256) return 32;
+    return 6;
+}
+
+// CSR5B200_OPT_SIGMA_RULE = 1: the table measured on B200 (profiles/r02_sigma_rule.md), replacing the reference's
+// Maxwell-era one above.  Same input (k = nnz / m) so that it stays a drop-in for setSigma(AUTO).
+int auto_sigma_b200(int m, int nnz, int value_bytes)
+{
+    const int k = m > 0 ? nnz / m : 0;
+    (void)value_bytes;
     if (k <= 4) return 4;
     if (k <= 32) return k;
     if (k <= 256) return 32;
@@ -201,7 +223,9 @@ int csr5b200_set_x(csr5b200_handle_t h, void *x)
 int csr5b200_set_sigma(csr5b200_handle_t h, int sigma)
 {
     if (!h) return CSR5B200_INVALID_ARGUMENT;
-    h->pl.sigma = sigma == CSR5B200_AUTO_TUNED_SIGMA ? auto_sigma(h->pl.m, h->pl.nnz) : sigma;
+    if (sigma == CSR5B200_AUTO_TUNED_SIGMA)
+        sigma = h->sigma_rule == 1 ? auto_sigma_b200(h->pl.m, h->pl.nnz, h->pl.value_bytes) : auto_sigma(h->pl.m, h->pl.nnz);
+    h->pl.sigma = sigma;
     return CSR5B200_SUCCESS;
 }
 
@@ -229,6 +253,10 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
         case CSR5B200_OPT_HOT_COLUMNS: h->tune.hot_columns = value; break;
         case CSR5B200_OPT_HOT_THREADS: h->tune.hot_threads = value; break;
+        case CSR5B200_OPT_SIGMA_RULE:
+            if (value < 0 || value > 1) return CSR5B200_INVALID_ARGUMENT;
+            h->sigma_rule = value;
+            break;
         case CSR5B200_OPT_EXCHANGE:
             if (value < 0 || value > 2) return CSR5B200_INVALID_ARGUMENT;
             h->tune.exchange = value;
@@ -269,8 +297,11 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
     const size_t vb = (size_t)pl.value_bytes;
     void *scan_scratch = nullptr;
     const size_t scan_bytes = scan_scratch_bytes(pl.p);
+    bool transposed = false;
     auto fail = [&](cudaError_t e) {
-        cudaFree(scan_scratch);
+        // leave the caller's arrays as they were handed in: a failure after the in-place transpose was enqueued
+        // undoes it (the transpose is its own inverse pair r2c / c2r)
+        if (transposed && launch_transpose(pl, false, h->stream) == cudaSuccess) cudaStreamSynchronize(h->stream);
         release_csr5_arrays(h);
         return cuda_fail(h, e);
     };
@@ -280,18 +311,27 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
         if (e__ != cudaSuccess) return fail(e__);   \
     } while (0)
 
-    CUF(cudaMalloc(&pl.tile_ptr, (size_t)(pl.p + 1) * sizeof(uint32_t)));
-    CUF(cudaMalloc(&pl.desc, (size_t)pl.p * OMEGA * pl.num_packet * sizeof(uint32_t)));
-    CUF(cudaMalloc(&pl.desc_off_ptr, (size_t)(pl.p + 1) * sizeof(int)));
-    CUF(cudaMalloc(&pl.calibrator, (size_t)pl.p * vb));
-    CUF(cudaMalloc(&pl.dev_flags, 8 * sizeof(int)));
-    CUF(cudaMalloc(&scan_scratch, scan_bytes));
+    const auto host_t0 = std::chrono::steady_clock::now();
+    typedef csr5b200_handle_s HS;
+    CUF(pool_get(h, HS::POOL_TILE_PTR, (size_t)(pl.p + 1) * sizeof(uint32_t), reinterpret_cast<void **>(&pl.tile_ptr)));
+    CUF(pool_get(h, HS::POOL_DESC, (size_t)pl.p * OMEGA * pl.num_packet * sizeof(uint32_t), reinterpret_cast<void **>(&pl.desc)));
+    CUF(pool_get(h, HS::POOL_DESC_OFF_PTR, (size_t)(pl.p + 1) * sizeof(int), reinterpret_cast<void **>(&pl.desc_off_ptr)));
+    CUF(pool_get(h, HS::POOL_CALIBRATOR, (size_t)pl.p * vb, &pl.calibrator));
+    CUF(pool_get(h, HS::POOL_FLAGS, 8 * sizeof(int), reinterpret_cast<void **>(&pl.dev_flags)));
+    CUF(pool_get(h, HS::POOL_SCAN, scan_bytes, &scan_scratch));
+    for (auto &e : h->ev_conv)
+        if (!e) CUF(cudaEventCreate(&e));
+    h->convert_alloc_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
     CUF(cudaMemsetAsync(pl.dev_flags, 0, 8 * sizeof(int), h->stream));
     CUF(cudaMemsetAsync(pl.calibrator, 0, (size_t)pl.p * vb, h->stream));
 
+    CUF(cudaEventRecord(h->ev_conv[0], h->stream));
     CUF(launch_tile_ptr(pl, h->stream));
+    CUF(cudaEventRecord(h->ev_conv[1], h->stream));
     CUF(launch_tile_desc(pl, h->stream));
+    CUF(cudaEventRecord(h->ev_conv[2], h->stream));
     CUF(launch_scan_offsets(pl, scan_scratch, scan_bytes, h->stream));
+    CUF(cudaEventRecord(h->ev_conv[3], h->stream));
 
     // One blocking read-back (the reference does three, anonymouslib_cuda.h:166, format_cuda.h:331,342):
     // tail start, first tile's row, number of empty-row table entries, "any dirty tile" flag.
@@ -308,14 +348,24 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
     // first non-empty row.  (Empty rows of the tail are written by the tail warps.)
     pl.needs_zero_fill = (any_dirty || (tp_first & ROW_MASK) > 0) ? 1 : 0;
 
+    CUF(cudaEventRecord(h->ev_conv[4], h->stream));
     if (num_offsets > 0) {
-        CUF(cudaMalloc(&pl.desc_off, (size_t)num_offsets * sizeof(int)));
+        CUF(pool_get(h, HS::POOL_DESC_OFF, (size_t)num_offsets * sizeof(int), reinterpret_cast<void **>(&pl.desc_off)));
         CUF(launch_desc_offset(pl, h->stream));
     }
+    CUF(cudaEventRecord(h->ev_conv[5], h->stream));
+    transposed = true;
     CUF(launch_transpose(pl, true, h->stream));
+    CUF(cudaEventRecord(h->ev_conv[6], h->stream));
     CUF(cudaStreamSynchronize(h->stream));
-    cudaFree(scan_scratch);
-    scan_scratch = nullptr;
+    {
+        // device time of the phases: tile_ptr, tile_desc, scan, (read-back), desc_offset, transpose
+        static const int from[5] = {0, 1, 2, 4, 5};
+        for (int k = 0; k < 5; k++)
+            if (cudaEventElapsedTime(&h->convert_ms[k], h->ev_conv[from[k]], h->ev_conv[from[k] + 1]) != cudaSuccess)
+                h->convert_ms[k] = -1.f;
+        cudaGetLastError();
+    }
     {
         const int err = build_hot_table(h);
         if (err) {  // leave the caller's arrays as they were handed in: undo the transpose
@@ -324,6 +374,7 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
             return err;
         }
     }
+    h->convert_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
 #undef CUF
     h->format = CSR5B200_FORMAT_CSR5;
     return CSR5B200_SUCCESS;
@@ -346,7 +397,7 @@ int csr5b200_as_csr(csr5b200_handle_t h)
     return CSR5B200_SUCCESS;
 }
 
-static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void *const *y_dst, int multicast)
+static int spmv_impl(csr5b200_handle_t h, double alpha, double beta, void *y, int n_dst, void *const *y_dst, int multicast)
 {
     const ShardCtx *sh = nullptr;
     if (!h) return CSR5B200_INVALID_ARGUMENT;
@@ -357,18 +408,6 @@ static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void
     for (int k = 0; k < n_dst; k++)
         if (!y_dst[k]) return CSR5B200_INVALID_ARGUMENT;
     if (h->ignore_alpha) alpha = 1.0;
-    cudaError_t e;
-    h->tune.ev_begin = h->tune.ev_end = nullptr;
-    if (h->kernel_timing && h->ev_used + 2 <= 2 * MAX_TIMED_SPMV) {
-        while (h->ev.size() < h->ev_used + 2) {
-            cudaEvent_t ev;
-            CU(h, cudaEventCreate(&ev));
-            h->ev.push_back(ev);
-        }
-        h->tune.ev_begin = h->ev[h->ev_used];
-        h->tune.ev_end = h->ev[h->ev_used + 1];
-        h->ev_used += 2;
-    }
     if (n_dst > 0) {
         ShardCtx &s = h->shard;
         s.n_dst = n_dst;
@@ -376,24 +415,57 @@ static int spmv_impl(csr5b200_handle_t h, double alpha, void *y, int n_dst, void
         s.multicast = multicast;
         s.exchange = h->tune.exchange;
         sh = &s;
+        if (beta != 0.0) return CSR5B200_INVALID_ARGUMENT;
+        // fused scheme: carries are completed in y_local and re-sent from there, so the unicast destination list
+        // must contain y_local; otherwise the rows would never reach it -- use the push scheme instead
+        int exchange = s.exchange;
+        if (exchange == 0)
+            exchange = (!h->pl.needs_zero_fill && h->pl.m > 0 && (long long)h->pl.nnz / h->pl.m <= 64) ? 1 : 2;
+        if (exchange == 1 && !multicast) {
+            bool has_local = false;
+            for (int k = 0; k < n_dst; k++) has_local |= y_dst[k] == y;
+            if (!has_local) return CSR5B200_INVALID_ARGUMENT;
+        }
     }
+    cudaError_t e;
+    h->tune.ev_begin = h->tune.ev_end = nullptr;
+    // the main kernel is bracketed only when one is launched (p > 0, m > 0); the pair is kept only on success
+    const bool timed = h->kernel_timing && h->pl.m > 0 && h->pl.p > 0 && h->ev_used + 2 <= 2 * MAX_TIMED_SPMV;
+    if (timed) {
+        while (h->ev.size() < h->ev_used + 2) {
+            cudaEvent_t ev;
+            CU(h, cudaEventCreate(&ev));
+            h->ev.push_back(ev);
+        }
+        h->tune.ev_begin = h->ev[h->ev_used];
+        h->tune.ev_end = h->ev[h->ev_used + 1];
+    }
+    h->launches_per_spmv = 0;
+    const SpmvCall all;
     if (h->pl.value_bytes == 8)
-        e = launch_spmv_f64(h->pl, h->tune, alpha, static_cast<double *>(y), sh, h->stream, &h->kernel_in_use,
-                            &h->launches_per_spmv);
+        e = launch_spmv_part_f64(h->pl, h->tune, alpha, beta, static_cast<double *>(y), sh, all, h->stream,
+                                 &h->kernel_in_use, &h->launches_per_spmv);
     else
-        e = launch_spmv_f32(h->pl, h->tune, (float)alpha, static_cast<float *>(y), sh, h->stream,
-                            &h->kernel_in_use, &h->launches_per_spmv);
+        e = launch_spmv_part_f32(h->pl, h->tune, (float)alpha, (float)beta, static_cast<float *>(y), sh, all, h->stream,
+                                 &h->kernel_in_use, &h->launches_per_spmv);
+    h->tune.ev_begin = h->tune.ev_end = nullptr;
     if (e != cudaSuccess) return cuda_fail(h, e);
+    if (timed) h->ev_used += 2;
     return CSR5B200_SUCCESS;
 }
 
-int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y) { return spmv_impl(h, alpha, y, 0, nullptr, 0); }
+int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y) { return spmv_impl(h, alpha, 0.0, y, 0, nullptr, 0); }
+
+int csr5b200_spmv_axpby(csr5b200_handle_t h, double alpha, double beta, void *y)
+{
+    return spmv_impl(h, alpha, beta, y, 0, nullptr, 0);
+}
 
 int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, void *y_local, int n_dst, void *const *y_dst,
                           int dst_is_multicast)
 {
     if (n_dst < 1 || (dst_is_multicast && n_dst != 1)) return CSR5B200_INVALID_ARGUMENT;
-    return spmv_impl(h, alpha, y_local, n_dst, y_dst, dst_is_multicast ? 1 : 0);
+    return spmv_impl(h, alpha, 0.0, y_local, n_dst, y_dst, dst_is_multicast ? 1 : 0);
 }
 
 int csr5b200_destroy(csr5b200_handle_t h)
@@ -419,6 +491,9 @@ int csr5b200_destroy(csr5b200_handle_t h)
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     h->s_in = h->s_out = nullptr;
+    h->batch_ready = false;
+    release_exchange(h);
+    free_pool(h);
     return err;
 }
 
@@ -458,6 +533,11 @@ int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out)
     out->launches_per_spmv = h->launches_per_spmv;
     out->hot_columns = pl.hot_k;
     out->hot_coverage = pl.hot_coverage;
+    for (int k = 0; k < 8; k++) out->convert_phase_ms[k] = h->convert_ms[k];
+    out->convert_host_ms = h->convert_host_ms;
+    out->convert_alloc_ms = h->convert_alloc_ms;
+    out->exchange_transport = h->ex.last_transport;
+    out->exchange_chunks = h->ex.last_chunks;
     return CSR5B200_SUCCESS;
 }
 
@@ -521,16 +601,17 @@ int csr5b200_spmv_host_batch(csr5b200_handle_t h, double alpha, int count, const
     if (count == 0) return CSR5B200_SUCCESS;
     const size_t vb = (size_t)h->pl.value_bytes;
     const size_t xbytes = (size_t)h->pl.n * vb, ybytes = (size_t)h->pl.m * vb;
-    if (!h->s_in) {
-        CU(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-        CU(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    if (!h->batch_ready) {   // set only once every resource exists: a partial failure is retried from where it stopped
+        if (!h->s_in) CU(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        if (!h->s_out) CU(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
         for (int b = 0; b < 2; b++) {
-            CU(h, cudaMalloc(&h->xb[b], xbytes ? xbytes : 1));
-            CU(h, cudaMalloc(&h->yb[b], ybytes ? ybytes : 1));
-            CU(h, cudaEventCreateWithFlags(&h->e_in[b], cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&h->e_comp[b], cudaEventDisableTiming));
-            CU(h, cudaEventCreateWithFlags(&h->e_out[b], cudaEventDisableTiming));
+            if (!h->xb[b]) CU(h, cudaMalloc(&h->xb[b], xbytes ? xbytes : 1));
+            if (!h->yb[b]) CU(h, cudaMalloc(&h->yb[b], ybytes ? ybytes : 1));
+            if (!h->e_in[b]) CU(h, cudaEventCreateWithFlags(&h->e_in[b], cudaEventDisableTiming));
+            if (!h->e_comp[b]) CU(h, cudaEventCreateWithFlags(&h->e_comp[b], cudaEventDisableTiming));
+            if (!h->e_out[b]) CU(h, cudaEventCreateWithFlags(&h->e_out[b], cudaEventDisableTiming));
         }
+        h->batch_ready = true;
     }
     // work already queued on the handle's stream (e.g. a previous spmv) precedes the pipeline
     CU(h, cudaEventRecord(h->e_comp[0], h->stream));

@@ -1,0 +1,383 @@
+// csr5_exchange.cu -- the step of a row-range sharded SpMV: csr5b200_spmv_allgather (include/csr5_b200.h).
+//
+// No reference counterpart (the reference is single-device).  What BASELINE.json's north_star
+// asks for -- "y segments concatenated over NVLink" -- is an all-gather of (N-1)/N of y INTO every GPU per step,
+// as large as the SpMV's own HBM stream once N >= 4, so it must run WHILE the SpMV runs:
+//
+//   handle stream S   [prologue] [tiles blk 0]      [tiles blk 2]      ...                      [wait all] [exit barrier]
+//   work1             .          .     [tiles blk 1]      [tiles blk 3] ...
+//   side              [entry barrier]  [carry 0][ship 0] [carry 1][ship 1] ...
+//   ce[k] (k != rank) .                        [copy 0 -> k]      [copy 1 -> k] ...     (COPY_ENGINE transport only)
+//
+// Row blocks are independent (a row is stored once, by the tile in which it starts; a block's carry pass only
+// touches rows that started in it or earlier), so consecutive blocks go to two alternating streams and overlap
+// at their edges -- no partial-wave bubble per block.  After block c and its carry pass, every row below the row
+// that holds the first non-zero of block c + 1 is final and can leave.
+#include <chrono>
+#include <cstdio>
+
+#include "csr5_handle.h"
+
+namespace csr5 {
+
+namespace {
+
+struct FlagPtrs {
+    uint32_t *p[CSR5B200_MAX_SCATTER];
+};
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One CTA of 32 threads; thread k talks to rank k.
+__global__ void flag_barrier_kernel(const FlagPtrs fp, const int rank, const int world, const int slot,
+                                    uint32_t *epoch, int *status, const unsigned long long timeout_ns)
+{
+    if (world <= 0) return;   // module warm-up launch
+    __shared__ uint32_t s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = epoch[slot] + 1;
+        epoch[slot] = s_epoch;
+    }
+    __syncthreads();
+    const uint32_t e = s_epoch;
+    const int k = threadIdx.x;
+    if (k >= world) return;
+    // Everything this GPU enqueued before the barrier (kernels, peer copies) has completed; publish it.
+    __threadfence_system();
+    uint32_t *theirs = fp.p[k] + slot * world + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(e) : "memory");
+    const uint32_t *mine = fp.p[rank] + slot * world + k;
+    const unsigned long long t0 = global_ns();
+    unsigned backoff = 32;
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - e) >= 0) break;
+        if (global_ns() - t0 > timeout_ns) { atomicExch(status, 1); break; }
+        __nanosleep(backoff);
+        if (backoff < 1024) backoff <<= 1;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_flag_barrier(uint32_t *const *flags, int rank, int world, int slot, uint32_t *epoch, int *status,
+                                int timeout_ms, cudaStream_t stream)
+{
+    FlagPtrs fp;
+    for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) fp.p[k] = (flags && k < world) ? flags[k] : nullptr;
+    flag_barrier_kernel<<<1, 32, 0, stream>>>(fp, rank, world, slot, epoch, status,
+                                              (unsigned long long)(timeout_ms > 0 ? timeout_ms : 20000) * 1000000ull);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_push_rows_f64(const void *, void *const *, int, int, long long, int, cudaStream_t);
+cudaError_t launch_push_rows_f32(const void *, void *const *, int, int, long long, int, cudaStream_t);
+
+cudaError_t launch_push_rows(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
+                             long long rows, int grid, cudaStream_t stream)
+{
+    return value_bytes == 8 ? launch_push_rows_f64(y_local, dst, n_dst, multicast, rows, grid, stream)
+                            : launch_push_rows_f32(y_local, dst, n_dst, multicast, rows, grid, stream);
+}
+
+void release_exchange(csr5b200_handle_t h)
+{
+    ExchangeState &x = h->ex;
+    auto ds = [](cudaStream_t &s) { if (s) cudaStreamDestroy(s); s = nullptr; };
+    auto de = [](cudaEvent_t &e) { if (e) cudaEventDestroy(e); e = nullptr; };
+    ds(x.work1);
+    ds(x.side);
+    for (auto &s : x.ce) ds(s);
+    de(x.ev_begin);
+    de(x.ev_side_done);
+    de(x.ev_work1_done);
+    for (auto &e : x.ev_chunk) de(e);
+    for (auto &e : x.ev_cal) de(e);
+    for (auto &e : x.ev_ce_done) de(e);
+    cudaFree(x.epoch);
+    cudaFree(x.status);
+    x = ExchangeState();
+}
+
+namespace {
+
+#define CUX(call)                                                  \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return handle_cuda_fail(h, e__);   \
+    } while (0)
+
+int ensure_state(csr5b200_handle_t h)
+{
+    ExchangeState &x = h->ex;
+    if (x.ready) return CSR5B200_SUCCESS;
+    int lo = 0, hi = 0;
+    CUX(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = greatest priority (numerically lowest)
+    CUX(cudaStreamCreateWithPriority(&x.work1, cudaStreamNonBlocking, lo));
+    // the shipping stream outranks the SpMV so that its small kernels get SM slots as soon as CTAs retire
+    CUX(cudaStreamCreateWithPriority(&x.side, cudaStreamNonBlocking, hi));
+    for (auto &s : x.ce) CUX(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+    const unsigned fl = cudaEventDisableTiming;
+    CUX(cudaEventCreateWithFlags(&x.ev_begin, fl));
+    CUX(cudaEventCreateWithFlags(&x.ev_side_done, fl));
+    CUX(cudaEventCreateWithFlags(&x.ev_work1_done, fl));
+    for (auto &e : x.ev_chunk) CUX(cudaEventCreateWithFlags(&e, fl));
+    for (auto &e : x.ev_cal) CUX(cudaEventCreateWithFlags(&e, fl));
+    for (auto &e : x.ev_ce_done) CUX(cudaEventCreateWithFlags(&e, fl));
+    CUX(cudaMalloc(&x.epoch, 2 * sizeof(uint32_t)));
+    CUX(cudaMalloc(&x.status, sizeof(int)));
+    CUX(cudaMemset(x.epoch, 0, 2 * sizeof(uint32_t)));
+    CUX(cudaMemset(x.status, 0, sizeof(int)));
+    x.ready = true;
+    return CSR5B200_SUCCESS;
+}
+
+// Row-block boundaries: equal tile counts; rows from tile_ptr (one small blocking read-back, cached).
+int ensure_chunks(csr5b200_handle_t h, int chunks)
+{
+    ExchangeState &x = h->ex;
+    const Plan &pl = h->pl;
+    const int ntiles = pl.p > 0 ? pl.p - 1 : 0;
+    if (chunks > MAX_CHUNKS) chunks = MAX_CHUNKS;
+    if (chunks > ntiles) chunks = ntiles;
+    if (chunks < 1) chunks = 1;
+    if (x.chunks == chunks && (int)x.chunk_tile.size() == chunks + 1) return CSR5B200_SUCCESS;
+    x.chunk_tile.assign(chunks + 1, 0);
+    x.chunk_row.assign(chunks + 1, 0);
+    for (int c = 0; c <= chunks; c++) x.chunk_tile[c] = (int)((long long)ntiles * c / chunks);
+    x.chunk_row[chunks] = pl.m;
+    std::vector<uint32_t> tp(chunks + 1, 0);
+    for (int c = 1; c < chunks; c++)
+        CUX(cudaMemcpyAsync(&tp[c], pl.tile_ptr + x.chunk_tile[c], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaStreamSynchronize(h->stream));
+    for (int c = 1; c < chunks; c++) x.chunk_row[c] = (int)(tp[c] & ROW_MASK);
+    x.chunks = chunks;
+    return CSR5B200_SUCCESS;
+}
+
+cudaError_t spmv_part(csr5b200_handle_t h, double alpha, double beta, void *y, const ShardCtx *sh, const SpmvCall &call,
+                      cudaStream_t stream)
+{
+    if (h->pl.value_bytes == 8)
+        return launch_spmv_part_f64(h->pl, h->tune, alpha, beta, static_cast<double *>(y), sh, call, stream,
+                                    &h->kernel_in_use, &h->launches_per_spmv);
+    return launch_spmv_part_f32(h->pl, h->tune, (float)alpha, (float)beta, static_cast<float *>(y), sh, call, stream,
+                                &h->kernel_in_use, &h->launches_per_spmv);
+}
+
+}  // namespace
+
+}  // namespace csr5
+
+using namespace csr5;
+
+extern "C" {
+
+int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, const csr5b200_exchange *ex)
+{
+    if (!h || !ex) return CSR5B200_INVALID_ARGUMENT;
+    if (h->format == CSR5B200_FORMAT_CSR) return CSR5B200_UNSUPPORTED_CSR_SPMV;
+    if (h->format != CSR5B200_FORMAT_CSR5) return CSR5B200_UNKNOWN_FORMAT;
+    const Plan &pl = h->pl;
+    const int world = ex->world, rank = ex->rank;
+    if (world < 1 || world > CSR5B200_MAX_SCATTER || rank < 0 || rank >= world || ex->row_begin < 0)
+        return CSR5B200_INVALID_ARGUMENT;
+    if (!pl.x && pl.nnz > 0) return CSR5B200_INVALID_ARGUMENT;
+    for (int k = 0; k < world; k++)
+        if (!ex->y_full[k]) return CSR5B200_INVALID_ARGUMENT;
+    bool barriers = world > 1;
+    for (int k = 0; k < world; k++)
+        if (!ex->flags[k]) barriers = false;
+    int transport = ex->transport;
+    if (transport < 0 || transport > CSR5B200_TRANSPORT_NONE) return CSR5B200_INVALID_ARGUMENT;
+    if (transport == CSR5B200_TRANSPORT_AUTO) transport = CSR5B200_TRANSPORT_COPY_ENGINE;
+    if (transport == CSR5B200_TRANSPORT_SM_MULTICAST && !ex->y_multicast) return CSR5B200_INVALID_ARGUMENT;
+    if (world == 1) transport = CSR5B200_TRANSPORT_NONE;
+    if (transport == CSR5B200_TRANSPORT_IN_KERNEL && beta != 0.0) return CSR5B200_INVALID_ARGUMENT;
+    if (h->ignore_alpha) alpha = 1.0;
+    int err = ensure_state(h);
+    if (err) return err;
+    ExchangeState &x = h->ex;
+    const size_t vb = (size_t)pl.value_bytes;
+    char *y_local = static_cast<char *>(ex->y_full[rank]) + (size_t)ex->row_begin * vb;
+    cudaStream_t S = h->stream;
+    h->launches_per_spmv = 0;
+    h->tune.ev_begin = h->tune.ev_end = nullptr;
+
+    if (pl.m <= 0 || pl.p == 0) {   // nothing to compute: clear / scale the rows, then only the barriers
+        SpmvCall all;
+        CUX(spmv_part(h, alpha, beta, y_local, nullptr, all, S));
+        if (barriers) {
+            if (ex->entry_barrier) {
+                CUX(launch_flag_barrier(ex->flags, rank, world, 0, x.epoch, x.status, ex->timeout_ms, S));
+                ++h->launches_per_spmv;
+            }
+            if (pl.m > 0 && transport != CSR5B200_TRANSPORT_NONE)
+                for (int k = 0; k < world; k++)
+                    if (k != rank)
+                        CUX(cudaMemcpyAsync(static_cast<char *>(ex->y_full[k]) + (size_t)ex->row_begin * vb, y_local,
+                                            (size_t)pl.m * vb, cudaMemcpyDefault, S));
+            CUX(launch_flag_barrier(ex->flags, rank, world, 1, x.epoch, x.status, ex->timeout_ms, S));
+            ++h->launches_per_spmv;
+        }
+        x.last_transport = transport;
+        x.last_chunks = 0;
+        return CSR5B200_SUCCESS;
+    }
+
+    int chunks = ex->chunks > 0 ? ex->chunks : 8;
+    if (transport == CSR5B200_TRANSPORT_IN_KERNEL || transport == CSR5B200_TRANSPORT_NONE) chunks = 1;
+    if ((err = ensure_chunks(h, chunks))) return err;
+    chunks = x.chunks;
+    const int push_ctas = ex->push_ctas > 0 ? ex->push_ctas : 32;
+
+    if (!x.warmed) {
+        // Load every module of the step now: CUDA loads kernels lazily at their first launch, and that load
+        // synchronises the context -- against a barrier kernel that is spinning for a peer it would deadlock.
+        // One throw-away SpMV into a scratch vector (y itself must stay what the caller handed in when beta != 0).
+        void *scratch = nullptr;
+        CUX(cudaMalloc(&scratch, (size_t)pl.m * vb));
+        SpmvCall all;
+        cudaError_t e = spmv_part(h, alpha, beta, scratch, nullptr, all, S);
+        void *none[CSR5B200_MAX_SCATTER] = {};
+        if (e == cudaSuccess) e = launch_push_rows((int)vb, scratch, none, 0, 0, pl.m < 1024 ? pl.m : 1024, 1, S);
+        if (e == cudaSuccess) e = launch_flag_barrier(nullptr, 0, 0, 0, x.epoch, x.status, 0, S);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(S);
+        cudaFree(scratch);
+        if (e != cudaSuccess) return handle_cuda_fail(h, e);
+        x.warmed = true;
+        h->launches_per_spmv = 0;
+    }
+
+    // ---- legacy scheme inside the new step: the SpMV kernel stores to every destination itself ----------------
+    if (transport == CSR5B200_TRANSPORT_IN_KERNEL) {
+        void *dst[CSR5B200_MAX_SCATTER];
+        for (int k = 0; k < world; k++) dst[k] = static_cast<char *>(ex->y_full[k]) + (size_t)ex->row_begin * vb;
+        ShardCtx sh;
+        sh.n_dst = world;
+        sh.y_dst = dst;
+        sh.multicast = 0;
+        sh.exchange = 1;
+        if (barriers && ex->entry_barrier) {
+            CUX(launch_flag_barrier(ex->flags, rank, world, 0, x.epoch, x.status, ex->timeout_ms, S));
+            ++h->launches_per_spmv;
+        }
+        SpmvCall all;
+        CUX(spmv_part(h, alpha, 0.0, y_local, &sh, all, S));
+        if (barriers) {
+            CUX(launch_flag_barrier(ex->flags, rank, world, 1, x.epoch, x.status, ex->timeout_ms, S));
+            ++h->launches_per_spmv;
+        }
+        x.last_transport = transport;
+        x.last_chunks = 1;
+        return CSR5B200_SUCCESS;
+    }
+
+    // ---- prologue on S, then fork ---------------------------------------------------------------------------------
+    {
+        SpmvCall pro;
+        pro.tiles = pro.calibrate = false;
+        CUX(spmv_part(h, alpha, beta, y_local, nullptr, pro, S));
+    }
+    CUX(cudaEventRecord(x.ev_begin, S));
+    CUX(cudaStreamWaitEvent(x.side, x.ev_begin, 0));
+    if (chunks > 1) CUX(cudaStreamWaitEvent(x.work1, x.ev_begin, 0));
+    const bool ship = transport != CSR5B200_TRANSPORT_NONE;
+    if (barriers && ex->entry_barrier && ship) {
+        CUX(launch_flag_barrier(ex->flags, rank, world, 0, x.epoch, x.status, ex->timeout_ms, x.side));
+        ++h->launches_per_spmv;
+    }
+    if (ship && transport == CSR5B200_TRANSPORT_COPY_ENGINE)
+        for (int k = 0; k < world; k++)
+            if (k != rank) CUX(cudaStreamWaitEvent(x.ce[k], x.ev_begin, 0));
+
+    void *dst[CSR5B200_MAX_SCATTER] = {};
+    int n_dst = 0;
+    for (int c = 0; c < chunks; c++) {
+        cudaStream_t W = (c & 1) ? x.work1 : S;
+        SpmvCall blk;
+        blk.tile_begin = x.chunk_tile[c];
+        blk.tile_end = x.chunk_tile[c + 1];
+        blk.tail = c == chunks - 1;
+        blk.prologue = false;
+        blk.calibrate = false;
+        CUX(spmv_part(h, alpha, beta, y_local, nullptr, blk, W));
+        CUX(cudaEventRecord(x.ev_chunk[c], W));
+
+        // carry pass of the block, then its finished rows leave
+        CUX(cudaStreamWaitEvent(x.side, x.ev_chunk[c], 0));
+        SpmvCall cal = blk;
+        cal.tiles = false;
+        cal.calibrate = true;
+        CUX(spmv_part(h, alpha, beta, y_local, nullptr, cal, x.side));
+        const long long ra = x.chunk_row[c], rb = x.chunk_row[c + 1];
+        if (!ship || rb <= ra) continue;
+        const char *src = y_local + (size_t)ra * vb;
+        const size_t off = ((size_t)ex->row_begin + (size_t)ra) * vb;
+        if (transport == CSR5B200_TRANSPORT_COPY_ENGINE) {
+            CUX(cudaEventRecord(x.ev_cal[c], x.side));
+            for (int k = 0; k < world; k++) {
+                if (k == rank) continue;
+                CUX(cudaStreamWaitEvent(x.ce[k], x.ev_cal[c], 0));
+                CUX(cudaMemcpyAsync(static_cast<char *>(ex->y_full[k]) + off, src, (size_t)(rb - ra) * vb,
+                                    cudaMemcpyDefault, x.ce[k]));
+                ++h->launches_per_spmv;
+            }
+        } else {
+            if (transport == CSR5B200_TRANSPORT_SM_MULTICAST) {
+                dst[0] = static_cast<char *>(ex->y_multicast) + off;
+                n_dst = 1;
+            } else {
+                n_dst = 0;
+                for (int k = 0; k < world; k++)
+                    if (k != rank) dst[n_dst++] = static_cast<char *>(ex->y_full[k]) + off;
+            }
+            CUX(launch_push_rows((int)vb, src, dst, n_dst, transport == CSR5B200_TRANSPORT_SM_MULTICAST, rb - ra,
+                                 push_ctas, x.side));
+            ++h->launches_per_spmv;
+        }
+    }
+
+    // ---- join --------------------------------------------------------------------------------------------------
+    if (chunks > 1) {
+        CUX(cudaEventRecord(x.ev_work1_done, x.work1));
+        CUX(cudaStreamWaitEvent(S, x.ev_work1_done, 0));
+    }
+    CUX(cudaEventRecord(x.ev_side_done, x.side));
+    CUX(cudaStreamWaitEvent(S, x.ev_side_done, 0));
+    if (ship && transport == CSR5B200_TRANSPORT_COPY_ENGINE)
+        for (int k = 0; k < world; k++) {
+            if (k == rank) continue;
+            CUX(cudaEventRecord(x.ev_ce_done[k], x.ce[k]));
+            CUX(cudaStreamWaitEvent(S, x.ev_ce_done[k], 0));
+        }
+    if (barriers) {
+        CUX(launch_flag_barrier(ex->flags, rank, world, 1, x.epoch, x.status, ex->timeout_ms, S));
+        ++h->launches_per_spmv;
+    }
+    x.last_transport = transport;
+    x.last_chunks = chunks;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_exchange_status(csr5b200_handle_t h)
+{
+    if (!h) return CSR5B200_INVALID_ARGUMENT;
+    CUX(cudaStreamSynchronize(h->stream));
+    if (!h->ex.ready) return CSR5B200_SUCCESS;
+    int st = 0;
+    CUX(cudaMemcpy(&st, h->ex.status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        CUX(cudaMemset(h->ex.status, 0, sizeof(int)));
+        return CSR5B200_EXCHANGE_TIMEOUT;
+    }
+    return CSR5B200_SUCCESS;
+}
+
+}  // extern "C"

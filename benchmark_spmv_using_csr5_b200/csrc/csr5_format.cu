@@ -37,6 +37,23 @@ __device__ __forceinline__ int count_le(const int *__restrict__ a, int n, int ke
     return lo;
 }
 
+// first index i in [0, n) with a[i] >= key (n if none)
+__device__ __forceinline__ int first_ge(const int *__restrict__ a, int n, long long key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if ((long long)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// A tile whose rows [start, stop] number more than this is not walked row by row: long runs of empty rows (R-MAT:
+// half of all rows) would serialise one warp over up to millions of rows.  Such a tile looks its <= omega * sigma
+// positions up by binary search instead (the reference's own formulation, format_cuda.h:362-422), which is bounded
+// by sigma * log2(span) probes per lane whatever the span.
+constexpr uint32_t WALK_LIMIT = 2048;
+
 // tile_ptr[t] = row that holds nnz index min(t * omega * sigma, nnz), last such row on ties.
 __global__ void tile_ptr_kernel(const int *__restrict__ row_ptr, uint32_t *__restrict__ tile_ptr,
                                 int *__restrict__ desc_off_ptr, int sigma, int p, int m, int nnz)
@@ -78,25 +95,46 @@ tile_desc_kernel(const int *__restrict__ row_ptr, uint32_t *tile_ptr, uint32_t *
         return;
     }
 
-    s_flags[w][lane] = 0;
-    __syncwarp();
     bool dirty = false;
-    for (uint32_t r0 = start; r0 <= stop; r0 += 32) {
-        const uint32_t r = r0 + lane;
-        if (r <= stop && r < (uint32_t)m) {
-            const int o = row_ptr[r];
-            const int o1 = row_ptr[r + 1];
-            if (r < stop && o == o1) dirty = true;  // rows [start, stop) as format_cuda.h:72-84
-            const long long pos = (long long)o - base;
-            if (pos >= 0 && pos < tile) {
-                const int ps = (int)pos;
-                atomicOr(&s_flags[w][ps / sigma], 1u << (ps % sigma));
+    uint32_t f = 0;  // bit i = element (lane, i) starts a row
+    if (stop - start <= WALK_LIMIT) {
+        s_flags[w][lane] = 0;
+        __syncwarp();
+        for (uint32_t r0 = start; r0 <= stop; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            if (r <= stop && r < (uint32_t)m) {
+                const int o = row_ptr[r];
+                const int o1 = row_ptr[r + 1];
+                if (r < stop && o == o1) dirty = true;  // rows [start, stop) as format_cuda.h:72-84
+                const long long pos = (long long)o - base;
+                if (pos >= 0 && pos < tile) {
+                    const int ps = (int)pos;
+                    atomicOr(&s_flags[w][ps / sigma], 1u << (ps % sigma));
+                }
+            }
+        }
+        __syncwarp();
+        f = s_flags[w][lane];
+    } else {
+        // rows r in [start, R], R = min(stop, m - 1); row_ptr[R + 1] exists.  Position `pos` carries a flag iff some
+        // row has row_ptr == base + pos; a second row with the same value means the first one is empty, and it lies
+        // below `stop` (the last row of the run is <= R), i.e. the tile is dirty.
+        const uint32_t R = stop < (uint32_t)m ? stop : (uint32_t)m - 1;
+        const int *a = row_ptr + start;
+        const int cnt = (int)(R - start) + 2;   // a[0 .. cnt): rows start .. R + 1
+        for (int i = 0; i <= sigma; i++) {
+            // lane l looks up its own sigma positions; position `tile` (the next tile's first element: empty rows
+            // that share it are still rows of this tile) is lane 31's extra round
+            if (i == sigma && lane != 31) break;
+            const long long v = base + (long long)lane * sigma + i;
+            const int k = first_ge(a, cnt, v);
+            if (k < cnt - 1 && (long long)a[k] == v) {
+                if (i < sigma) f |= 1u << i;
+                if ((long long)a[k + 1] == v) dirty = true;
             }
         }
     }
-    __syncwarp();
     dirty = __any_sync(FULL, dirty);
-    const uint32_t f = s_flags[w][lane];  // bit i = element (lane, i) starts a row
 
     int y_off = 0, seg_off = 0, total = 0;
     if (t < p - 1) {
@@ -247,6 +285,25 @@ desc_offset_kernel(const int *__restrict__ row_ptr, const uint32_t *__restrict__
     __syncwarp();
 
     const int ob = desc_off_ptr[t];
+    if (stop - start > WALK_LIMIT) {
+        // bounded form for tiles that span long runs of empty rows: every flagged element finds the row that starts
+        // there -- the LAST row with that row_ptr value -- by binary search (format_cuda.h:362-422)
+        const int *a = row_ptr + start + 1;
+        const int cnt = (int)(stop - start);     // rows start + 1 .. stop
+        uint32_t mine = f;
+        if (lane == 0) mine &= ~1u;
+        const int yo = (int)(w0 >> (32 - bit_y));
+        int k = 0;
+        while (mine) {
+            const int i = __ffs(mine) - 1;
+            mine &= mine - 1;
+            const long long v = base + (long long)lane * sigma + i;
+            const int r = first_ge(a, cnt, v + 1) - 1;   // last row (relative to start + 1) with row_ptr <= v
+            desc_off[ob + yo + k] = r;
+            k++;
+        }
+        return;
+    }
     for (uint32_t r0 = start + 1; r0 <= stop; r0 += 32) {
         const uint32_t r = r0 + lane;
         if (r <= stop) {

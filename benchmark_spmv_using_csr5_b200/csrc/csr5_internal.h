@@ -93,13 +93,36 @@ struct ShardCtx {
     int exchange = 0;               // 0 auto, 1 fused (SpMV kernels store to every destination), 2 push (copy pass after)
 };
 
-// Enqueues [clear y] + compute(+tail) + calibrate; in sharded mode (sh != nullptr) the rows are also
-// delivered to every destination (fused into the kernels, or by a copy pass).  y is the result vector in local memory.  Returns the
-// kernel variant used in *used.
-cudaError_t launch_spmv_f64(const Plan &pl, const SpmvTuning &tn, double alpha, double *y, const ShardCtx *sh,
-                            cudaStream_t stream, int *used, int *launches);
-cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, const ShardCtx *sh,
-                            cudaStream_t stream, int *used, int *launches);
+// Which parts of an SpMV one launch group enqueues.  A whole spmv() = everything on over all tiles; the
+// overlapped multi-GPU exchange (csr5_exchange.cu) cuts the tiles into row blocks.
+struct SpmvCall {
+    int tile_begin = 0;     // CSR5 tiles [tile_begin, tile_end) of [0, p - 1); tile_end < 0 = up to p - 1
+    int tile_end = -1;
+    bool tail = true;       // also the rows of the tail tile (p - 1)
+    bool prologue = true;   // clear (beta = 0) / scale (beta != 0) the rows no tile stores; refresh the hot-column table
+    bool tiles = true;      // the main kernel over the tiles (+ tail)
+    bool calibrate = true;  // the carry pass over the same tiles (+ the tail tile's carry)
+};
+
+// Enqueues the selected parts of y = alpha * A * x + beta * y; in the legacy sharded mode (sh != nullptr) the rows
+// are also delivered to every destination (fused into the kernels, or by a copy pass).  y is the result vector in
+// local memory.  Returns the kernel variant used in *used; *launches is incremented per enqueued node.
+cudaError_t launch_spmv_part_f64(const Plan &pl, const SpmvTuning &tn, double alpha, double beta, double *y,
+                                 const ShardCtx *sh, const SpmvCall &call, cudaStream_t stream, int *used, int *launches);
+cudaError_t launch_spmv_part_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float beta, float *y,
+                                 const ShardCtx *sh, const SpmvCall &call, cudaStream_t stream, int *used, int *launches);
+// SM transport of the overlapped exchange: coalesced copy of `rows` rows from y_local to dst[0..n_dst) (peer
+// addresses, or one NVSwitch multicast address) with `grid` CTAs.
+cudaError_t launch_push_rows(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
+                             long long rows, int grid, cudaStream_t stream);
+
+// ---- cross-GPU barrier on flag words in peer-mapped memory (csr5_exchange.cu) ------------------------------
+// flags[k] = base of rank k's flag array as mapped here (>= 2 * world words each, zero-initialised).  Rank r
+// bumps its own epoch counter (device word), writes it to word [slot * world + r] of every rank, and waits until
+// every word [slot * world + k] of its OWN array has reached it.  Bounded: gives up after timeout_ms and raises
+// *status (device word) instead of hanging the GPU.
+cudaError_t launch_flag_barrier(uint32_t *const *flags, int rank, int world, int slot, uint32_t *epoch,
+                                int *status, int timeout_ms, cudaStream_t stream);
 
 }  // namespace csr5
 

@@ -55,10 +55,12 @@ struct SpmvArgs {
     const int *__restrict__ desc_off;
     VT *__restrict__ cal;
     VT alpha;
+    VT beta;             // y = alpha * A * x + beta * y (0: y is overwritten and never read)
     int m, p, bit_y, bit_all, num_packet;
+    int tile_begin, tile_end;  // CSR5 tiles [tile_begin, tile_end) of [0, p - 1) this launch processes
     int tail_start;      // first row of the tail tile
     int tail_nnz_start;  // (p - 1) * omega * sigma
-    int tail_warps;      // ceil((m - tail_start) / 32)
+    int tail_warps;      // ceil((m - tail_start) / 32) when this launch also does the tail rows, else 0
     // Sharded (multi-GPU) mode (csr5b200_spmv_scatter): `y` is this rank's segment in local HBM; the
     // n_dst destination segments -- this rank's slot in each GPU's concatenated y, mapped over NVLink,
     // or ONE NVSwitch multicast address that replicates a store to all of them -- receive copies.
@@ -77,6 +79,10 @@ template <> __device__ __forceinline__ void multimem_store<float>(float *p, floa
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
+template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
 // All y stores of the SpMV kernels go through put_y.  MULTI = false: the plain local store.  MULTI = true
 // (sharded mode, "fused" exchange): the value is stored to every destination instead -- each GPU's copy
 // of the concatenated y over NVLink, or once to the NVSwitch multicast address -- so the all-gather
@@ -85,6 +91,9 @@ template <bool MULTI, typename VT>
 __device__ __forceinline__ void put_y(const SpmvArgs<VT> &a, int row, VT v)
 {
     if constexpr (!MULTI) {
+        // every row is stored exactly once per SpMV (by the tile in which it starts, or by the tail), so
+        // the beta * y term is a plain read-modify-write here; carries are added afterwards
+        if (a.beta != (VT)0) v = fma_t<VT>(a.beta, a.y[row], v);
         a.y[row] = v;
     } else {
         if (a.dst_multicast) {
@@ -98,10 +107,6 @@ __device__ __forceinline__ void put_y(const SpmvArgs<VT> &a, int row, VT v)
 }
 
 // ---- small device helpers ---------------------------------------------------------------------
-
-template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
-template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
-template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
 template <typename VT> __device__ __forceinline__ VT warp_sum_xor(VT v)
 {
@@ -343,8 +348,8 @@ __global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT
     const int lane = threadIdx.x & 31;
     const long long unit = (long long)blockIdx.x * WPB + (threadIdx.x >> 5);
     if (unit < a.tail_warps) { process_tail_rows<VT, MULTI>(a, (int)unit, lane); return; }
-    const long long tl = unit - a.tail_warps;
-    if (tl >= a.p - 1) return;
+    const long long tl = a.tile_begin + (unit - a.tail_warps);
+    if (tl >= a.tile_end) return;
     const int t = (int)tl;
     const size_t base = (size_t)t * (OMEGA * SIGMA);
     GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet};
@@ -435,7 +440,8 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
     // tail rows first (they are few); warps stride over them
     for (long long tw = gw; tw < a.tail_warps; tw += GW) process_tail_rows<VT, false>(a, (int)tw, lane);
 
-    const long long ntiles = a.p - 1;
+    const long long ntiles = a.tile_end;          // this launch: tiles [tile_begin, tile_end)
+    const long long first = a.tile_begin + gw;    // this warp's first tile
     const uint32_t desc_bytes = OMEGA * 4 * a.num_packet;
     const uint32_t tx_bytes = Slot::VAL_BYTES + Slot::COL_BYTES + desc_bytes;
     const uint64_t policy = l2_evict_first_policy();
@@ -453,16 +459,16 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
 
     // prologue: fill the ring
     if (lane == 0) {
-        long long t = gw;
+        long long t = first;
         for (int s = 0; s < stages && t < ntiles; s++, t += GW) issue(t, s);
     }
     uint32_t raw_start = 0, raw_stop = 0;
-    if (gw < ntiles) { raw_start = __ldg(a.tile_ptr + gw); raw_stop = __ldg(a.tile_ptr + gw + 1); }
+    if (first < ntiles) { raw_start = __ldg(a.tile_ptr + first); raw_stop = __ldg(a.tile_ptr + first + 1); }
 
     int s = 0;
     uint32_t parity = 0;
     if constexpr (!PREFETCH) {
-        for (long long t = gw; t < ntiles; t += GW) {
+        for (long long t = first; t < ntiles; t += GW) {
             // tile_ptr words of the next tile are fetched one iteration ahead
             const long long tn = t + GW;
             uint32_t nstart = 0, nstop = 0;
@@ -490,13 +496,13 @@ __global__ void __launch_bounds__(TMA_MAX_WARPS * 32, 1) spmv_tma_kernel(const S
         VT xc[SIGMA], xn[SIGMA];
 #pragma unroll
         for (int i = 0; i < SIGMA; i++) { xc[i] = (VT)0; xn[i] = (VT)0; }
-        if (gw < ntiles) {  // x of this warp's first tile
+        if (first < ntiles) {  // x of this warp's first tile
             mbar_wait(smem_u32(bars), 0);
             const int *col0 = reinterpret_cast<const int *>(my_slots + Slot::VAL_BYTES);
 #pragma unroll
             for (int i = 0; i < SIGMA; i++) xc[i] = __ldg(a.x + col0[i * OMEGA + lane]);
         }
-        for (long long t = gw; t < ntiles; t += GW) {
+        for (long long t = first; t < ntiles; t += GW) {
             const long long tn = t + GW;
             int sn = s + 1;
             uint32_t pn = parity;
@@ -577,8 +583,8 @@ spmv_hot_kernel(const SpmvArgs<VT> a, const VT *__restrict__ hot_x, const uint32
     const long long GW = (long long)gridDim.x * wpb;
     const long long gw = (long long)blockIdx.x * wpb + (threadIdx.x >> 5);
     for (long long tw = gw; tw < a.tail_warps; tw += GW) process_tail_rows<VT, MULTI>(a, (int)tw, lane);
-    const long long ntiles = a.p - 1;
-    for (long long tl = gw; tl < ntiles; tl += GW) {
+    const long long ntiles = a.tile_end;
+    for (long long tl = a.tile_begin + gw; tl < ntiles; tl += GW) {
         const int t = (int)tl;
         const size_t base = (size_t)t * (OMEGA * SIGMA);
         HotTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet, xs};
@@ -588,10 +594,10 @@ spmv_hot_kernel(const SpmvArgs<VT> a, const VT *__restrict__ hot_x, const uint32
 
 // ---- carries: y[row of tile t] += calibrator[t] for the tiles whose first row began earlier -----
 template <typename VT>
-__global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a)
+__global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a, const int t_begin, const int t_end)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.p) return;
+    const int t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_end) return;
     const VT c = a.cal[t];
     if (c != (VT)0) atomicAdd(a.y + (a.tile_ptr[t] & ROW_MASK), c);   // local HBM only, also when sharded
 }
@@ -666,6 +672,14 @@ __global__ void __launch_bounds__(256) zero_empty_rows_kernel(const SpmvArgs<VT>
         if (__ldg(a.row_ptr + r) == __ldg(a.row_ptr + r + 1)) put_y<true, VT>(a, (int)r, (VT)0);
 }
 
+// y = alpha A x + beta y: the rows no tile stores (empty rows in front of the tail) only get the beta term
+template <typename VT>
+__global__ void __launch_bounds__(256) scale_empty_rows_kernel(const SpmvArgs<VT> a, const int row_limit)
+{
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < row_limit; r += (long long)gridDim.x * blockDim.x)
+        if (__ldg(a.row_ptr + r) == __ldg(a.row_ptr + r + 1)) a.y[r] = a.beta * a.y[r];
+}
+
 // sharded mode, "fused" exchange: rows that received carries are complete in local HBM only after
 // calibrate_kernel; the last tile of each such row re-sends the final value to every destination (plain
 // stores -- no atomics cross NVLink).
@@ -694,8 +708,8 @@ template <typename VT, int SIGMA>
 cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_ok, cudaStream_t stream,
                          int *used, int hot_k, const VT *hot_x, bool multi)
 {
-    const long long ntiles = a.p - 1;
-    if (hot_k > 0 && ntiles > 0) {
+    const long long ntiles = (long long)a.tile_end - a.tile_begin;   // CSR5 tiles of this launch
+    if (hot_k > 0 && (ntiles > 0 || a.tail_warps > 0)) {
         // column indices are tagged: only the hot-column kernel can read them
         const uint32_t hot_bytes = (uint32_t)(((size_t)hot_k * sizeof(VT) + 15) / 16 * 16);
         const size_t smem = hot_bytes + 16;
@@ -724,6 +738,7 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
     if (kernel == 0) kernel = 1;
     if ((kernel == 2 || kernel == 4) && !tma_ok) kernel = 1;
     if (ntiles <= 0 || multi) kernel = 1;  // the multi-destination (sharded) variant exists for the direct kernel
+    if (kernel != 1 && a.beta != (VT)0) kernel = 1;   // beta * y is wired into the direct-load kernel's stores
     *used = kernel;
 
     if (kernel == 1) {
@@ -786,22 +801,24 @@ cudaError_t launch_sigma(const SpmvArgs<VT> &a, const SpmvTuning &tn, bool tma_o
     return kernel == 4 ? run(spmv_tma_kernel<VT, SIGMA, true>) : run(spmv_tma_kernel<VT, SIGMA, false>);
 }
 
+// One group of launches of an SpMV: any subset of {prologue, tiles [tile_begin, tile_end) (+ tail rows), carry pass of the
+// same tiles}.  A whole spmv() is one call with everything on; the overlapped multi-GPU exchange cuts the tiles
+// into row blocks and issues the parts on different streams (csr5_exchange.cu).
 template <typename VT>
-cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y, const ShardCtx *sh,
-                          cudaStream_t stream, int *used, int *launches)
+cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT beta, VT *y, const ShardCtx *sh,
+                               const SpmvCall &call, cudaStream_t stream, int *used, int *launches)
 {
-    *used = 0;
-    *launches = 0;
     if (pl.m <= 0) return cudaSuccess;
     const int n_dst = sh ? sh->n_dst : 0;
     if (n_dst < 0 || n_dst > CSR5B200_MAX_SCATTER) return cudaErrorInvalidValue;
-    // exchange of the sharded mode: fused = the SpMV kernels store to every destination; push = one coalesced
-    // copy pass after the SpMV.  Auto: fused when each tile stores runs of consecutive rows (no empty rows,
-    // short rows), push when the row stores are scattered (dirty tiles, long rows).
+    // exchange of the legacy sharded mode (csr5b200_spmv_scatter): fused = the SpMV kernels store to every
+    // destination; push = one coalesced copy pass after the SpMV.  Auto: fused when each tile stores runs of
+    // consecutive rows (no empty rows, short rows), push when the row stores are scattered.
     int exchange = sh ? sh->exchange : 0;
     if (sh && exchange == 0)
         exchange = (!pl.needs_zero_fill && pl.m > 0 && (long long)pl.nnz / pl.m <= 64) ? 1 : 2;
     const bool fused = exchange == 1;
+    if (fused && beta != (VT)0) return cudaErrorNotSupported;
     cudaError_t e;
     SpmvArgs<VT> a;
     a.n_dst = n_dst;
@@ -819,6 +836,7 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
     a.desc_off = pl.desc_off;
     a.cal = static_cast<VT *>(pl.calibrator);
     a.alpha = alpha;
+    a.beta = beta;
     a.m = pl.m;
     a.p = pl.p;
     a.bit_y = pl.bit_y;
@@ -826,29 +844,41 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
     a.num_packet = pl.num_packet;
     a.tail_start = pl.tail_start;
     a.tail_nnz_start = pl.p > 0 ? (pl.p - 1) * OMEGA * pl.sigma : 0;
-    a.tail_warps = pl.p > 0 ? (pl.m - pl.tail_start + 31) / 32 : 0;
+    const int ntiles_all = pl.p > 0 ? pl.p - 1 : 0;
+    a.tile_begin = call.tile_begin < 0 ? 0 : call.tile_begin;
+    a.tile_end = call.tile_end < 0 || call.tile_end > ntiles_all ? ntiles_all : call.tile_end;
+    if (a.tile_begin > a.tile_end) a.tile_begin = a.tile_end;
+    const bool tail = call.tail && pl.p > 0;
+    a.tail_warps = tail ? (pl.m - pl.tail_start + 31) / 32 : 0;
+    const int threads = 256;
 
-    if (pl.needs_zero_fill || pl.p == 0) {
-        if (fused) {
-            zero_empty_rows_kernel<VT><<<tn.num_sms * 8, 256, 0, stream>>>(a);
-            e = cudaGetLastError();
-        } else {
-            e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
+    if (call.prologue) {
+        // rows that no tile and no tail warp stores: the empty rows in front of the tail
+        if (pl.needs_zero_fill || pl.p == 0) {
+            if (fused) {
+                zero_empty_rows_kernel<VT><<<tn.num_sms * 8, 256, 0, stream>>>(a);
+                e = cudaGetLastError();
+            } else if (beta != (VT)0) {
+                scale_empty_rows_kernel<VT><<<tn.num_sms * 8, 256, 0, stream>>>(a, pl.p == 0 ? pl.m : pl.tail_start);
+                e = cudaGetLastError();
+            } else {
+                e = cudaMemsetAsync(y, 0, (size_t)pl.m * sizeof(VT), stream);
+            }
+            if (e != cudaSuccess) return e;
+            ++*launches;
         }
-        if (e != cudaSuccess) return e;
-        ++*launches;
-    }
-    if (pl.p > 0) {
-        // bulk TMA needs 16-byte aligned global addresses; tile strides are multiples of 128 bytes
-        const bool tma_ok = (reinterpret_cast<uintptr_t>(a.val) % 16 == 0) &&
-                            (reinterpret_cast<uintptr_t>(a.col) % 16 == 0) &&
-                            (reinterpret_cast<uintptr_t>(a.desc) % 16 == 0);
         if (pl.hot_k > 0 && pl.p > 1) {
             hot_gather_kernel<VT><<<(pl.hot_k + 255) / 256, 256, 0, stream>>>(a.x, pl.hot_col,
                                                                             static_cast<VT *>(pl.hot_x), pl.hot_k);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             ++*launches;
         }
+    }
+    if (call.tiles && pl.p > 0 && (a.tile_end > a.tile_begin || a.tail_warps > 0)) {
+        // bulk TMA needs 16-byte aligned global addresses; tile strides are multiples of 128 bytes
+        const bool tma_ok = (reinterpret_cast<uintptr_t>(a.val) % 16 == 0) &&
+                            (reinterpret_cast<uintptr_t>(a.col) % 16 == 0) &&
+                            (reinterpret_cast<uintptr_t>(a.desc) % 16 == 0);
         if (tn.ev_begin && (e = cudaEventRecord(tn.ev_begin, stream)) != cudaSuccess) return e;
         switch (pl.sigma) {
 #define CSR5_CASE(S) case S: e = launch_sigma<VT, S>(a, tn, tma_ok, stream, used, pl.hot_k, static_cast<const VT *>(pl.hot_x), fused); break;
@@ -863,15 +893,19 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
         if (e != cudaSuccess) return e;
         if (tn.ev_end && (e = cudaEventRecord(tn.ev_end, stream)) != cudaSuccess) return e;
         ++*launches;
-        const int threads = 256;
-        calibrate_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);   // local HBM only
-        ++*launches;
+    }
+    if (call.calibrate && pl.p > 0) {
+        const int cb = a.tile_begin, ce = tail ? pl.p : a.tile_end;   // the tail tile's carry is calibrator[p - 1]
+        if (ce > cb) {
+            calibrate_kernel<VT><<<(ce - cb + threads - 1) / threads, threads, 0, stream>>>(a, cb, ce);   // local HBM only
+            ++*launches;
+        }
         if (fused) {
             push_carried_rows_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a);
             ++*launches;
         }
     }
-    if (sh && !fused) {
+    if (sh && !fused && call.calibrate) {
         PushArgs<VT> pa;
         pa.y_local = y;
         for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) pa.dst[k] = a.y_dst[k];
@@ -881,6 +915,23 @@ cudaError_t launch_spmv_t(const Plan &pl, const SpmvTuning &tn, VT alpha, VT *y,
         push_rows_kernel<VT><<<tn.num_sms * 4, PUSH_THREADS, 0, stream>>>(pa);
         ++*launches;
     }
+    return cudaGetLastError();
+}
+
+// Coalesced copy of `rows` finished rows of y (local HBM) to the same rows of every destination: the SM transport
+// of the overlapped exchange.  `grid` CTAs only -- it shares the GPU with the SpMV of the next row block.
+template <typename VT>
+cudaError_t launch_push_t(const VT *y_local, VT *const *dst, int n_dst, int multicast, long long rows, int grid,
+                          cudaStream_t stream)
+{
+    if (rows <= 0) return cudaSuccess;
+    PushArgs<VT> pa;
+    pa.y_local = y_local;
+    for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) pa.dst[k] = k < n_dst ? dst[k] : nullptr;
+    pa.n_dst = n_dst;
+    pa.multicast = multicast;
+    pa.m = (int)rows;
+    push_rows_kernel<VT><<<grid, PUSH_THREADS, 0, stream>>>(pa);
     return cudaGetLastError();
 }
 

@@ -1,10 +1,16 @@
-// FP32 instantiations of the CSR5 SpMV kernels (sigma 4..32, direct-load and TMA-staged).
+// FP32 instantiations of the CSR5 SpMV kernels (sigma 4..32: direct-load, TMA-staged, hot-column).
 #include "csr5_spmv.cuh"
 
 namespace csr5 {
-cudaError_t launch_spmv_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float *y, const ShardCtx *sh,
-                            cudaStream_t stream, int *used, int *launches)
+cudaError_t launch_spmv_part_f32(const Plan &pl, const SpmvTuning &tn, float alpha, float beta, float *y,
+                                 const ShardCtx *sh, const SpmvCall &call, cudaStream_t stream, int *used, int *launches)
 {
-    return launch_spmv_t<float>(pl, tn, alpha, y, sh, stream, used, launches);
+    return launch_spmv_part_t<float>(pl, tn, alpha, beta, y, sh, call, stream, used, launches);
+}
+cudaError_t launch_push_rows_f32(const void *y_local, void *const *dst, int n_dst, int multicast, long long rows,
+                                 int grid, cudaStream_t stream)
+{
+    return launch_push_t<float>(static_cast<const float *>(y_local), reinterpret_cast<float *const *>(dst), n_dst, multicast,
+                             rows, grid, stream);
 }
 }  // namespace csr5

@@ -48,7 +48,14 @@ OPT_DIRECT_NCH = 8
 OPT_HOT_COLUMNS = 9
 OPT_HOT_THREADS = 10
 OPT_EXCHANGE = 11
+OPT_SIGMA_RULE = 12
+SIGMA_RULE_REFERENCE, SIGMA_RULE_B200 = 0, 1
 EXCHANGE_AUTO, EXCHANGE_FUSED, EXCHANGE_PUSH = 0, 1, 2
+# csr5b200_spmv_allgather transports (CSR5B200_TRANSPORT_*)
+TRANSPORT_AUTO, TRANSPORT_COPY_ENGINE, TRANSPORT_SM_PUSH, TRANSPORT_SM_MULTICAST, TRANSPORT_IN_KERNEL, TRANSPORT_NONE = range(6)
+TRANSPORT_NAMES = {"auto": 0, "ce": 1, "push": 2, "multicast": 3, "inkernel": 4, "none": 5}
+EXCHANGE_TIMEOUT = -102
+PROBES = {"stream": 1, "gather_nc": 2, "gather_cg": 3, "gather_ca": 4, "gather_only": 5, "fma_noseg": 6}
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TMA, KERNEL_HOT, KERNEL_TMA_PREFETCH = 0, 1, 2, 3, 4
 
 
@@ -118,6 +125,21 @@ class anonymouslibHandle:
         self._bind_stream()
         return self._lib.csr5b200_spmv(self._h, float(alpha), _ptr(y))
 
+    def spmv_axpby(self, alpha: float, beta: float, y) -> int:
+        """y = alpha * A * x + beta * y (csr5b200_spmv_axpby; the reference's commented-out `beta`,
+        anonymouslib_cuda.h:281)."""
+        _check_dev(y, self.dtype, "y", self.m)
+        self._bind_stream()
+        return self._lib.csr5b200_spmv_axpby(self._h, float(alpha), float(beta), _ptr(y))
+
+    def spmv_allgather(self, alpha: float, beta: float, exchange: "_lib.Csr5Exchange") -> int:
+        """One step of a row-range sharded SpMV with the y exchange overlapped (csr5b200_spmv_allgather)."""
+        self._bind_stream()
+        return self._lib.csr5b200_spmv_allgather(self._h, float(alpha), float(beta), C.byref(exchange))
+
+    def exchange_status(self) -> int:
+        return self._lib.csr5b200_exchange_status(self._h)
+
     def spmv_scatter(self, alpha: float, y_local, y_dst, n_dst: int, multicast: bool = False) -> int:
         """Sharded mode (csr5b200_spmv_scatter): ``y_local`` is this shard's y segment (CUDA tensor in local
         memory), ``y_dst`` a ctypes array of ``n_dst`` device pointers, each the address of this shard's
@@ -156,6 +178,14 @@ class anonymouslibHandle:
         xs = (C.c_void_p * k)(*[self._host_ptr(a, self.n) for a in x_hosts])
         ys = (C.c_void_p * k)(*[self._host_ptr(a, self.m) for a in y_hosts])
         return self._lib.csr5b200_spmv_host_batch(self._h, float(alpha), k, xs, ys)
+
+    def probe(self, kind: int, repeats: int = 20) -> float:
+        """csr5b200_probe: mean device ms of one stripped-down launch (PROBE_* kinds)."""
+        ms = C.c_float(0)
+        err = self._lib.csr5b200_probe(self._h, int(kind), int(repeats), C.byref(ms))
+        if err:
+            raise RuntimeError(self.error_string(err))
+        return float(ms.value)
 
     def info(self) -> _lib.Csr5Info:
         out = _lib.Csr5Info()

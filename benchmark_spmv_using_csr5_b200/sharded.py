@@ -7,18 +7,25 @@ nnz -- the same "row that holds nnz index b" search as the reference's tile part
 boundaries b = g * nnz / G -- every rank builds its OWN CSR5 arrays for its rows through the
 ordinary handle, x is replicated, and the y segments are concatenated on every rank.
 
-Two exchange modes:
+This module is a binding: the step itself is ``csr5b200_spmv_allgather`` of the C ABI
+(csrc/csr5_exchange.cu); torch only provides the symmetric (peer-mapped) memory and the process group.
 
-* ``"fused"`` (default): the concatenated y lives in symmetric memory (every rank's buffer mapped
-  into every process over NVLink/NVSwitch) and ``csr5b200_spmv_scatter`` delivers this rank's rows to
-  ALL of them -- through ONE store to the NVSwitch multicast address when the fabric offers it
-  (``multicast=True``, the default when available), else through one store per peer.  ``scheme`` 1:
-  the SpMV kernels themselves store each finished row to the destinations as tiles complete, so the
-  all-gather traffic overlaps the tile stream; ``scheme`` 2: the SpMV runs on local memory and one
-  coalesced pass pushes the segment (16-byte stores); 0 = auto by row structure.  One device-side
-  barrier ends the step.  No NCCL call on the data path.
-* ``"nccl"``: local SpMV into this rank's slot, then an all-gather(-v) over NCCL (the baseline the
-  fused mode is measured against; also what runs on gloo in the CPU tests of the host logic).
+Exchange modes:
+
+* ``"overlap"`` (default): the concatenated y lives in symmetric memory, TWO buffers used alternately.
+  The shard's tiles are cut into row blocks that stream through the SpMV kernel while the finished
+  blocks travel to the peers -- by the copy engines (``transport="ce"``), by a small grid of pushing
+  CTAs (``"push"``), or through the NVSwitch multicast address (``"multicast"``).  Device-side flag
+  barriers end the step; no NCCL call and no host synchronisation on the data path.  Because the
+  buffers alternate, the y returned by step k stays valid until step k + 2 is enqueued, and a rank may
+  run ahead into step k + 1 while its peers still read y_k (the write-after-read hazard of a single
+  buffer).
+* ``"fused"``: the first-generation scheme (``csr5b200_spmv_scatter``): every finished row is stored
+  to all GPUs from inside the SpMV kernel (``scheme`` 1) or pushed by one coalesced pass afterwards
+  (``scheme`` 2); kept for A/B measurements.  A barrier BEFORE the stores (all peers are done with the
+  previous y) and one after them bracket the step.
+* ``"nccl"``: local SpMV into this rank's slot, then an all-gather(-v) over NCCL (the baseline; also
+  what runs on gloo in the CPU tests of the host logic).
 """
 from __future__ import annotations
 
@@ -95,42 +102,76 @@ class ShardedCsr5:
     """This rank's row range of a sharded matrix.  ``local_row_ptr`` is rebased to 0; ``bounds`` are
     the G + 1 global row boundaries (``row_partition``); ``n`` is the global column count."""
 
-    def __init__(self, bounds, n: int, local_row_ptr, col, val, group=None, mode: str = "fused",
-                 sigma: int = -1, multicast: bool | None = None, scheme: int = 0):
+    def __init__(self, bounds, n: int, local_row_ptr, col, val, group=None, mode: str = "overlap",
+                 sigma: int = -1, multicast: bool | None = None, scheme: int = 0, transport: str | int = "auto",
+                 chunks: int = 0, push_ctas: int = 0, timeout_ms: int = 0):
         import torch
         import torch.distributed as dist
+        from . import _lib
         from . import handle as H
-        self._torch, self._dist, self._H = torch, dist, H
+        self._torch, self._dist, self._H, self._lib = torch, dist, H, _lib
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bounds = np.asarray(bounds, np.int64)
         if len(self.bounds) != self.world + 1:
             raise ValueError("bounds must have world_size + 1 entries")
-        if self.world > MAX_SCATTER and mode == "fused":
-            raise ValueError(f"fused mode supports up to {MAX_SCATTER} ranks")
+        if mode not in ("overlap", "fused", "nccl"):
+            raise ValueError(f"unknown exchange mode {mode!r}")
+        if self.world > MAX_SCATTER and mode != "nccl":
+            raise ValueError(f"{mode} mode supports up to {MAX_SCATTER} ranks")
         self.m_global = int(self.bounds[-1])
         self.row_begin, self.row_end = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
         self.m_local = self.row_end - self.row_begin
         self.n = int(n)
         self.dtype = val.dtype
-        self.mode = mode
+        self.mode = mode if self.world > 1 else "local"
         self.h = H.anonymouslibHandle(self.m_local, self.n, self.dtype)
         err = self.h.inputCSR(int(col.numel()), local_row_ptr, col, val)
         if err:
             raise RuntimeError(self.h.error_string(err))
         self.h.setSigma(sigma)
-        self.scheme = int(scheme)   # 0 auto, 1 stores fused into the SpMV kernels, 2 coalesced push pass
+        self.scheme = int(scheme)   # fused mode: 0 auto, 1 stores fused into the SpMV kernels, 2 coalesced push pass
+        self.transport = H.TRANSPORT_NAMES[transport] if isinstance(transport, str) else int(transport)
+        self.chunks, self.push_ctas, self.timeout_ms = int(chunks), int(push_ctas), int(timeout_ms)
         self._resolved = False
         self._symm = None
         self._dst = None
+        self._parity = 0
         self.multicast = False
         dev = val.device
-        if mode == "fused" and self.world > 1:
+        item = torch.empty(0, dtype=self.dtype).element_size()
+        if self.mode == "overlap":
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self._stride = (self.m_global + 31) // 32 * 32          # second buffer starts 128-byte aligned
+            self._ybuf = symm_mem.empty(2 * self._stride, dtype=self.dtype, device=dev)
+            self._symm = symm_mem.rendezvous(self._ybuf, grp)
+            self._flagbuf = symm_mem.empty(64, dtype=torch.int32, device=dev)
+            self._flagbuf.zero_()
+            self._fsymm = symm_mem.rendezvous(self._flagbuf, grp)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)                                     # every rank's flag words are zero before anyone signals
+            mc = int(self._symm.multicast_ptr or 0)
+            self._ex = []
+            for b in range(2):
+                ex = _lib.Csr5Exchange()
+                ex.rank, ex.world = self.rank, self.world
+                for k in range(self.world):
+                    ex.y_full[k] = int(self._symm.buffer_ptrs[k]) + b * self._stride * item
+                    ex.flags[k] = int(self._fsymm.buffer_ptrs[k])
+                ex.y_multicast = (mc + b * self._stride * item) if mc else None
+                ex.row_begin = self.row_begin
+                ex.entry_barrier = 0                                # two alternating buffers: see the module docstring
+                self._ex.append(ex)
+            self.has_multicast = bool(mc)
+            if self.transport == H.TRANSPORT_SM_MULTICAST and not mc:
+                raise RuntimeError("transport 'multicast': the fabric offers no multicast address")
+            self.y_full = self._ybuf[:self.m_global]
+        elif self.mode == "fused":
             import torch.distributed._symmetric_memory as symm_mem
             self.y_full = symm_mem.empty(self.m_global, dtype=self.dtype, device=dev)
             self._symm = symm_mem.rendezvous(self.y_full, group if group is not None else dist.group.WORLD)
-            item = self.y_full.element_size()
             mc = int(self._symm.multicast_ptr or 0)
             ptrs = [int(p) + self.row_begin * item for p in self._symm.buffer_ptrs]
             self._dst_unicast = (C.c_void_p * self.world)(*ptrs)
@@ -165,31 +206,169 @@ class ShardedCsr5:
         self._dst = self._dst_multicast if self.multicast else self._dst_unicast
         self._resolved = True
 
+    def _views(self, parity: int):
+        base = parity * self._stride
+        full = self._ybuf[base:base + self.m_global]
+        return full, full[self.row_begin:self.row_end]
+
     def spmv_local(self, alpha: float = 1.0) -> int:
         """Only this rank's rows (no exchange)."""
         return self.h.spmv(alpha, self.y_local)
 
-    def spmv(self, alpha: float = 1.0):
-        """y = alpha * A x, concatenated on every rank.  Returns the full y tensor (valid on the
-        current stream once the call's work has completed)."""
-        if self.world == 1:
-            err = self.h.spmv(alpha, self.y_local)
-        elif self._dst is not None:
+    def spmv(self, alpha: float = 1.0, beta: float = 0.0):
+        """y = alpha * A x (+ beta * y), concatenated on every rank.  Returns the full y tensor (valid on the
+        current stream once the call's work has completed; in overlap mode until the next-but-one call)."""
+        if self.mode == "overlap":
+            ex = self._ex[self._parity]
+            ex.transport, ex.chunks, ex.push_ctas, ex.timeout_ms = self.transport, self.chunks, self.push_ctas, self.timeout_ms
+            if beta != 0.0 and self._parity != self._last_parity():
+                # beta * y refers to the y of the previous step, which lives in the other buffer
+                prev_full, prev_local = self._views(self._last_parity())
+                self._views(self._parity)[1].copy_(prev_local)
+            err = self.h.spmv_allgather(alpha, beta, ex)
+            self.y_full, self.y_local = self._views(self._parity)
+            self._prev = self._parity
+            self._parity ^= 1
+        elif self.mode == "fused":
+            if beta != 0.0:
+                raise ValueError("fused mode has no beta term; use mode='overlap'")
             if not self._resolved:
                 self._resolve_exchange()
+            self._symm.barrier(channel=1)      # every peer is done reading the previous y before it is overwritten
             err = self.h.spmv_scatter(alpha, self.y_local, self._dst, len(self._dst), self.multicast)
             if not err:
                 self._symm.barrier(channel=0)  # all peers' stores have landed before anyone reads y
-        else:
-            err = self.h.spmv(alpha, self.y_local)
+        elif self.mode == "nccl":
+            err = self.h.spmv_axpby(alpha, beta, self.y_local) if beta != 0.0 else self.h.spmv(alpha, self.y_local)
             if not err:
                 allgather_v(self.y_full, self.bounds, self.rank, self.group)
+        else:
+            err = self.h.spmv_axpby(alpha, beta, self.y_local) if beta != 0.0 else self.h.spmv(alpha, self.y_local)
         if err:
             raise RuntimeError(self.h.error_string(err))
         return self.y_full
+
+    def _last_parity(self) -> int:
+        return getattr(self, "_prev", self._parity)
+
+    def iterate(self, steps: int, alpha: float = 1.0):
+        """x_{k+1} = alpha * A x_k for `steps` steps without leaving the devices: the gathered y of one step is
+        the x of the next (square matrices).  In overlap mode the two y buffers alternate as x and y, and the
+        exchange of step k overlaps its own SpMV; returns the last y."""
+        if self.m_global != self.n:
+            raise ValueError("iterate() needs a square matrix (y is fed back as x)")
+        y = None
+        for _ in range(int(steps)):
+            y = self.spmv(alpha)
+            if self.mode in ("fused", "nccl", "local"):
+                y = y.clone()   # one buffer: the next step overwrites it while it is being read as x
+            err = self.h.setX(y)
+            if err:
+                raise RuntimeError(self.h.error_string(err))
+        return y
+
+    def exchange_status(self) -> int:
+        """Synchronises; EXCHANGE_TIMEOUT if a device-side barrier gave up waiting for a peer."""
+        return self.h.exchange_status() if self.mode == "overlap" else 0
 
     def destroy(self) -> int:
         return self.h.destroy()
 
     def free(self):
         self.h.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# binding of the single-process C++ host API (include/csr5_b200_sharded.h)
+# ---------------------------------------------------------------------------------------------
+BARRIER_AUTO, BARRIER_FLAGS, BARRIER_EVENTS = 0, 1, 2
+
+
+class ShardedCsr5Native:
+    """``csr5b200_sharded_*``: all shards driven from this one process (one worker thread per shard inside the
+    library).  ``devices[s]`` is the CUDA device of shard s; listing a device twice puts two shards on it (how the
+    single-GPU test box exercises the path).  Host numpy arrays in, host numpy arrays out; no torch involved."""
+
+    def __init__(self, devices, dtype=np.float64):
+        from . import _lib
+        self._lib = _lib.load_library()
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("VALUE_TYPE must be float64 or float32")
+        self.devices = [int(d) for d in devices]
+        self._s = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        self._check(self._lib.csr5b200_sharded_create(len(self.devices), arr, self.dtype.itemsize, C.byref(self._s)))
+        self.m = self.n = 0
+
+    def _check(self, err):
+        if err:
+            raise RuntimeError(f"csr5b200_sharded: {self._lib.csr5b200_error_string(err).decode()} ({err})")
+
+    def inputCSR(self, m, n, row_ptr, col, val):
+        rp = np.ascontiguousarray(row_ptr, np.int32)
+        ci = np.ascontiguousarray(col, np.int32)
+        v = np.ascontiguousarray(val, self.dtype)
+        self.m, self.n = int(m), int(n)
+        self._check(self._lib.csr5b200_sharded_input_csr_host(self._s, self.m, self.n, int(ci.size), rp.ctypes.data,
+                                                              ci.ctypes.data, v.ctypes.data))
+
+    def setSigma(self, sigma=-1):
+        self._check(self._lib.csr5b200_sharded_set_sigma(self._s, int(sigma)))
+
+    def set_option(self, option, value):
+        self._check(self._lib.csr5b200_sharded_set_option(self._s, int(option), int(value)))
+
+    def set_exchange(self, transport=0, chunks=0, push_ctas=0, barrier=BARRIER_AUTO, timeout_ms=0):
+        from . import handle as H
+        t = H.TRANSPORT_NAMES[transport] if isinstance(transport, str) else int(transport)
+        self._check(self._lib.csr5b200_sharded_set_exchange(self._s, t, int(chunks), int(push_ctas), int(barrier),
+                                                            int(timeout_ms)))
+
+    def setX(self, x):
+        xx = np.ascontiguousarray(x, self.dtype)
+        if xx.size < self.n:
+            raise ValueError("x: needs n values")
+        self._check(self._lib.csr5b200_sharded_set_x_host(self._s, xx.ctypes.data))
+
+    def asCSR5(self):
+        self._check(self._lib.csr5b200_sharded_as_csr5(self._s))
+
+    def spmv(self, alpha=1.0, beta=0.0):
+        self._check(self._lib.csr5b200_sharded_spmv(self._s, float(alpha), float(beta)))
+
+    def iterate(self, steps, alpha=1.0):
+        self._check(self._lib.csr5b200_sharded_iterate(self._s, int(steps), float(alpha)))
+
+    def synchronize(self):
+        self._check(self._lib.csr5b200_sharded_synchronize(self._s))
+
+    def y(self, shard=0) -> np.ndarray:
+        """The concatenated y of the last step as shard `shard`'s device holds it (synchronises)."""
+        out = np.empty(self.m, self.dtype)
+        self._check(self._lib.csr5b200_sharded_copy_y_to_host(self._s, int(shard), out.ctypes.data))
+        return out
+
+    def bounds(self) -> np.ndarray:
+        b = (C.c_longlong * (len(self.devices) + 1))()
+        self._check(self._lib.csr5b200_sharded_get_bounds(self._s, b))
+        return np.array(list(b), np.int64)
+
+    def shard_info(self, shard):
+        from . import _lib
+        h = C.c_void_p()
+        self._check(self._lib.csr5b200_sharded_get_handle(self._s, int(shard), C.byref(h)))
+        out = _lib.Csr5Info()
+        self._check(self._lib.csr5b200_get_info(h, C.byref(out)))
+        return out
+
+    def destroy(self):
+        if self._s:
+            self._lib.csr5b200_sharded_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

@@ -79,6 +79,9 @@ CSR5B200_API int csr5b200_as_csr5(csr5b200_handle_t h);
 CSR5B200_API int csr5b200_set_x(csr5b200_handle_t h, void *x);
 /* int spmv(alpha, y)                                         anonymouslib_cuda.h:21, 262-285 */
 CSR5B200_API int csr5b200_spmv(csr5b200_handle_t h, double alpha, void *y);
+/* y = alpha * A * x + beta * y.  The reference's spmv() carries the stub of this form -- a commented-out `beta`
+ * argument in the csr5_spmv() call at anonymouslib_cuda.h:281 -- and never implements it.  beta = 0 is exactly spmv() (y is not read). */
+CSR5B200_API int csr5b200_spmv_axpby(csr5b200_handle_t h, double alpha, double beta, void *y);
 /* int destroy()   (asCSR + release of the CSR5 arrays)       anonymouslib_cuda.h:22, 287-292 */
 CSR5B200_API int csr5b200_destroy(csr5b200_handle_t h);
 /* void setSigma(sigma | ANONYMOUSLIB_AUTO_TUNED_SIGMA)       anonymouslib_cuda.h:23, 294-318 */
@@ -94,7 +97,7 @@ CSR5B200_API int csr5b200_set_sigma(csr5b200_handle_t h, int sigma);
  *             the enqueued work it holds the final rows like after spmv().
  *   y_dst[k]: address of THIS shard's first row inside destination k's concatenated y (device pointers;
  *             peers' buffers mapped into this process over NVLink, e.g. CUDA IPC / symmetric memory).  The
- *             list normally contains y_local itself.  With dst_is_multicast = 1, n_dst must be 1 and
+ *             list contains y_local itself (required by the fused scheme).  With dst_is_multicast = 1, n_dst must be 1 and
  *             y_dst[0] is an NVSwitch multicast address (multimem) covering all GPUs including this one.
  * Two exchange schemes (CSR5B200_OPT_EXCHANGE): "fused" -- the SpMV kernels store every finished row to all
  * destinations as tiles complete, so the NVLink traffic overlaps the tile stream; rows completed by carries
@@ -102,10 +105,59 @@ CSR5B200_API int csr5b200_set_sigma(csr5b200_handle_t h, int sigma);
  * cleared everywhere; "push" -- the SpMV runs on local memory and one coalesced pass then copies the segment
  * to every destination with 16-byte stores (for matrices whose row stores are scattered).  Auto picks fused
  * for matrices without empty rows and with short rows.  Everything is ordered on the handle's stream; the
- * caller synchronises the devices afterwards (a cross-GPU barrier) before anyone reads y.
+ * caller synchronises the devices afterwards (a cross-GPU barrier) before anyone reads y -- and BEFORE the call
+ * too if a peer may still be reading the y of the previous step (the stores land in the peers' buffers as soon as
+ * the kernel runs).  In the fused scheme y_dst[] MUST contain y_local (carries are completed in y_local and
+ * re-sent from there), else CSR5B200_INVALID_ARGUMENT.  Superseded by csr5b200_spmv_allgather below, which
+ * overlaps the exchange with the SpMV and brings its own barriers.
  * 1 <= n_dst <= CSR5B200_MAX_SCATTER.  Same return codes as spmv(). */
 CSR5B200_API int csr5b200_spmv_scatter(csr5b200_handle_t h, double alpha, void *y_local, int n_dst,
                                        void *const *y_dst, int dst_is_multicast);
+
+/* ---- overlapped all-gather: the step of a row-range sharded SpMV, one call per shard per step -----------------
+ *
+ * The shard's CSR5 tiles are cut into `chunks` row blocks.  The blocks stream through the SpMV kernel back to back
+ * (two alternating streams, so a block's last CTAs overlap the next block's first); as soon as a block's carries
+ * are in, its finished rows travel to every other GPU while the later blocks are still being computed:
+ *   COPY_ENGINE     one peer copy per destination on its own stream (DMA engines; no SM is involved),
+ *   SM_PUSH         a small grid (push_ctas CTAs) of 16-byte coalesced loads + one store per peer,
+ *   SM_MULTICAST    the same grid storing once to the NVSwitch multicast address (multimem.st),
+ *   IN_KERNEL       no row blocks: the SpMV kernel itself stores each finished row to every destination
+ *                   (the first-generation scheme of csr5b200_spmv_scatter; beta must be 0),
+ *   NONE            nothing is sent (y_full[rank] only receives this shard's rows).
+ * Two device-side barriers on flag words in peer-mapped memory bracket the remote writes: the ENTRY barrier
+ * (overlapped with the first row block) holds them back until every rank has finished the work it had enqueued
+ * before this call -- e.g. reading the previous y -- and the EXIT barrier ends the step: after it, on this
+ * handle's stream, y_full[rank] holds all rows of all shards.  Callers that alternate between two y buffers can
+ * drop the entry barrier (entry_barrier = 0); callers that synchronise the ranks themselves pass flags = NULLs.
+ * Every rank must make the same sequence of calls.  Barriers give up after timeout_ms (default 20 s) and
+ * csr5b200_exchange_status() then reports it -- a lost peer never hangs the GPU. */
+#define CSR5B200_TRANSPORT_AUTO         0
+#define CSR5B200_TRANSPORT_COPY_ENGINE  1
+#define CSR5B200_TRANSPORT_SM_PUSH      2
+#define CSR5B200_TRANSPORT_SM_MULTICAST 3
+#define CSR5B200_TRANSPORT_IN_KERNEL    4
+#define CSR5B200_TRANSPORT_NONE         5
+
+typedef struct csr5b200_exchange {
+    int rank, world;                        /* 1 <= world <= CSR5B200_MAX_SCATTER */
+    void *y_full[CSR5B200_MAX_SCATTER];     /* base of rank k's concatenated y as mapped in THIS process; [rank] is local */
+    void *y_multicast;                      /* NVSwitch multicast address of the same buffer, or NULL */
+    uint32_t *flags[CSR5B200_MAX_SCATTER];  /* rank k's barrier words (>= 2 * world, zeroed once) as mapped here; NULL = no barriers */
+    long long row_begin;                    /* first row of this shard inside the concatenated y */
+    int chunks;                             /* row blocks (0 = auto, at most 64) */
+    int transport;                          /* CSR5B200_TRANSPORT_* */
+    int entry_barrier;                      /* 1 = hold remote writes until all ranks reached this call */
+    int push_ctas;                          /* SM transports: CTAs of the push grid (0 = default 32) */
+    int timeout_ms;                         /* barrier time-out (0 = default 20000) */
+} csr5b200_exchange;
+
+/* y_full[rank][row_begin + i] = alpha * (A_shard x)_i + beta * (old value), i < m, delivered to every rank as
+ * described above.  Same return codes as spmv(). */
+CSR5B200_API int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, const csr5b200_exchange *ex);
+/* Synchronises the handle's stream; returns CSR5B200_EXCHANGE_TIMEOUT if a barrier gave up since the last call. */
+#define CSR5B200_EXCHANGE_TIMEOUT (-102)
+CSR5B200_API int csr5b200_exchange_status(csr5b200_handle_t h);
 
 /* Frees the handle object itself (the reference's handle is a stack object). Calls destroy(). */
 CSR5B200_API int csr5b200_free(csr5b200_handle_t h);
@@ -131,6 +183,9 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
 #define CSR5B200_OPT_HOT_THREADS   10 /* tuning: threads per CTA of the hot-column kernel (0 = default 768) */
 #define CSR5B200_OPT_EXCHANGE      11 /* spmv_scatter: 0 auto (default), 1 fused (the SpMV kernels store every finished row to
                                          all destinations), 2 push (one coalesced copy pass after the SpMV) */
+#define CSR5B200_OPT_SIGMA_RULE    12 /* what CSR5B200_AUTO_TUNED_SIGMA means at the next set_sigma(): 0 (default) the reference's
+                                         table r/s/t/u = 4/32/256/6 (anonymouslib_cuda.h:297-313; keeps the CSR5 arrays word for
+                                         word those of the reference), 1 the rule measured on B200 (profiles/r02_sigma_rule.md) */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays
@@ -157,6 +212,12 @@ typedef struct csr5b200_info {
     int launches_per_spmv; /* kernels (+ memset nodes) one spmv() enqueues */
     int hot_columns;       /* entries of the hot-column table in use (0 = none) */
     double hot_coverage;   /* fraction of the tiles' x references served by the table */
+    float convert_phase_ms[8]; /* device time of the phases of the last as_csr5(): [0] tile_ptr, [1] tile_desc,
+                                  [2] scan, [3] desc_offset, [4] transpose (in-place, col + val) */
+    double convert_host_ms;    /* host wall time of the last as_csr5() */
+    double convert_alloc_ms;   /* of which buffer (re)allocation; 0 when the handle's buffer pool already fits */
+    int exchange_transport;    /* csr5b200_spmv_allgather: transport and row blocks of the last step */
+    int exchange_chunks;
 } csr5b200_info;
 CSR5B200_API int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out);
 
@@ -164,6 +225,17 @@ CSR5B200_API int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out);
  * main SpMV kernel of the spmv() calls since the last call of this function, oldest first, at most
  * `capacity` (and at most 4096 are retained).  Synchronises the stream.  *count = number written. */
 CSR5B200_API int csr5b200_get_kernel_times(csr5b200_handle_t h, float *ms, int capacity, int *count);
+
+/* Microbenchmarks on the matrix held by the handle (CSR5 format, no hot-column table): the SpMV's launch shape and
+ * col stream with the kernel stripped down to one component, to MEASURE the floors quoted in DESIGN.md
+ * (csrc/csr5_probe.cu).  *ms_avg = mean device time of `repeats` launches.  Overwrites the calibrator array. */
+#define CSR5B200_PROBE_STREAM       1  /* val + col streamed, no x: the HBM floor of the matrix stream */
+#define CSR5B200_PROBE_GATHER_NC    2  /* col streamed + x[col] through ld.global.nc: the gather floor as the kernel issues it */
+#define CSR5B200_PROBE_GATHER_CG    3  /* ... through ld.global.cg */
+#define CSR5B200_PROBE_GATHER_CA    4  /* ... through ld.global.ca */
+#define CSR5B200_PROBE_GATHER_ONLY  5  /* no col stream: x[hash]: the pure divergent-gather rate out of L2 */
+#define CSR5B200_PROBE_FMA_NOSEG    6  /* val + col + x + FMA, no descriptors, no segmented sum, one store per tile */
+CSR5B200_API int csr5b200_probe(csr5b200_handle_t h, int kind, int repeats, float *ms_avg);
 
 /* Host copies of the CSR5 arrays (sizes as in csr5b200_info; NULL = skip that array).  Synchronous.
  * Test/diagnostic aid: lets a harness diff the metadata word for word without a CUDA binding. */

@@ -79,6 +79,10 @@ def lib():
         L.csr5o_csr_spmv_f64.restype = None
         L.csr5o_csr_spmv_f32.argtypes = [C.c_int, _i32p, _i32p, _f32p, _f32p, C.c_float, _f32p]
         L.csr5o_csr_spmv_f32.restype = None
+        L.csr5o_csr_axpby_f64.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, C.c_double, C.c_double, _f64p]
+        L.csr5o_csr_axpby_f64.restype = None
+        L.csr5o_csr_axpby_f32.argtypes = [C.c_int, _i32p, _i32p, _f32p, _f32p, C.c_float, C.c_float, _f32p]
+        L.csr5o_csr_axpby_f32.restype = None
         L.csr5o_csr_spmv_f32_acc64.argtypes = [C.c_int, _i32p, _i32p, _f32p, _f32p, _f64p]
         L.csr5o_csr_spmv_f32_acc64.restype = None
         _lib = L
@@ -249,6 +253,17 @@ def csr_spmv(m, row_ptr, col, val, x, alpha: float = 1.0) -> np.ndarray:
     f(m, np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col, np.int32), val,
       np.ascontiguousarray(x, val.dtype), alpha, y)
     return y
+
+
+def csr_axpby(m, row_ptr, col, val, x, alpha: float, beta: float, y) -> np.ndarray:
+    """alpha * A x + beta * y by the scalar CSR loop (the form stubbed at anonymouslib_cuda.h:281); returns a
+    new array, y is not modified."""
+    val = np.ascontiguousarray(val)
+    out = np.ascontiguousarray(y, val.dtype).copy()
+    f = lib().csr5o_csr_axpby_f64 if val.dtype == np.float64 else lib().csr5o_csr_axpby_f32
+    f(m, np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(col, np.int32), val,
+      np.ascontiguousarray(x, val.dtype), alpha, beta, out)
+    return out
 
 
 def csr_spmv_f32_acc64(m, row_ptr, col, val, x) -> np.ndarray:

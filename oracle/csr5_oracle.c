@@ -401,6 +401,29 @@ void csr5o_csr_spmv_f32(int m, const int *row_ptr, const int *col, const float *
     }
 }
 
+/* y = alpha * (A x) + beta * y -- the scalar statement of the form the reference's spmv() stubs out (the
+ * commented-out `beta` argument at anonymouslib_cuda.h:281, next to the alpha its kernels ignore,
+ * csr5_spmv_cuda.h:22).  Row sums as in main.cu:343-349. */
+void csr5o_csr_axpby_f64(int m, const int *row_ptr, const int *col, const double *val,
+                         const double *x, double alpha, double beta, double *y)
+{
+    for (int i = 0; i < m; i++) {
+        double sum = 0;
+        for (int j = row_ptr[i]; j < row_ptr[i + 1]; j++) sum += x[col[j]] * val[j];
+        y[i] = alpha * sum + beta * y[i];
+    }
+}
+
+void csr5o_csr_axpby_f32(int m, const int *row_ptr, const int *col, const float *val,
+                         const float *x, float alpha, float beta, float *y)
+{
+    for (int i = 0; i < m; i++) {
+        float sum = 0;
+        for (int j = row_ptr[i]; j < row_ptr[i + 1]; j++) sum += x[col[j]] * val[j];
+        y[i] = alpha * sum + beta * y[i];
+    }
+}
+
 /* FP32 inputs, FP64 accumulation: error yardstick for the FP32 configuration. */
 void csr5o_csr_spmv_f32_acc64(int m, const int *row_ptr, const int *col, const float *val,
                               const float *x, double *y)

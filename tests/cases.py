@@ -55,6 +55,18 @@ def small_cases():
     lap, _ = M.laplacian27(12)
     out.append(("lap27_12_auto", lap, -1))
     out.append(("all_sigmas_probe", M.from_row_counts(_counts(rng, 800, 0, 40), 800, 14), 19))
+    # runs of thousands of empty rows inside one tile's row span (R-MAT at scale: half of all rows are empty): the
+    # format kernels switch from walking the rows to binary searches beyond 2048 rows per tile
+    rng2 = np.random.default_rng(77)   # own stream: the cases above keep the inputs their golden vectors were made from
+    c = _counts(rng2, 12000, 1, 9)
+    c[100:4100] = 0
+    c[6000:9000] = 0
+    c[9000] = 700
+    c[-2500:] = 0
+    out.append(("long_empty_runs_s6", M.from_row_counts(c, 3000, 16), 6))
+    c = np.zeros(20000, np.int64)
+    c[::2500] = 40
+    out.append(("sparse_rows_huge_span_auto", M.from_row_counts(c, 500, 17), -1))
     return out
 
 

@@ -1,0 +1,227 @@
+"""GPU tests (-m gpu) of what round 2 adds around the SpMV, all through the C ABI and all runnable on ONE GPU:
+
+* y = alpha A x + beta y (csr5b200_spmv_axpby -- the reference's commented-out `beta`, anonymouslib_cuda.h:281)
+  against the oracle's scalar statement;
+* the overlapped all-gather step (csr5b200_spmv_allgather): row-block cut of the SpMV is bit-identical to the
+  one-launch SpMV for every chunk count, every transport delivers every shard's rows to every shard;
+* the single-process sharded handle (include/csr5_b200_sharded.h) with several shards on the same device -- the
+  multi-GPU code path (peer copies, push kernels, in-kernel stores, flag / event barriers, double-buffered y,
+  y -> x feedback) with device 0 standing in for every peer.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from benchmark_spmv_using_csr5_b200 import matrices as M
+from tests.cases import small_cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = small_cases()
+IDS = [c[0] for c in CASES]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _handle(torch, A, val, x, sigma):
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    tdt = torch.float64 if val.dtype == np.float64 else torch.float32
+    dev = "cuda"
+    keep = (torch.from_numpy(A.row_ptr).to(dev), torch.from_numpy(A.col).to(dev), torch.from_numpy(val).to(dev),
+            torch.from_numpy(x).to(dev))
+    h = H.anonymouslibHandle(A.m, A.n, tdt)
+    assert h.inputCSR(A.nnz, keep[0], keep[1], keep[2]) == 0
+    assert h.setX(keep[3]) == 0
+    h.setSigma(sigma)
+    assert h.asCSR5() == 0
+    return h, keep
+
+
+# ---- beta ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("name,A,sigma", CASES, ids=IDS)
+def test_axpby_matches_oracle(torch_cuda, oracle, name, A, sigma, dt):
+    torch = torch_cuda
+    rng = np.random.default_rng(5)
+    val, x = M.values(A.nnz, A.n, "int", dt)
+    y0 = rng.integers(-9, 10, size=A.m).astype(dt)
+    h, _keep = _handle(torch, A, val, x, sigma)
+    for alpha, beta in ((1.0, 1.0), (2.0, -3.0), (-1.0, 0.5), (3.0, 0.0)):
+        y = torch.from_numpy(y0.copy()).cuda()
+        assert h.spmv_axpby(alpha, beta, y) == 0
+        torch.cuda.synchronize()
+        want = oracle.csr_axpby(A.m, A.row_ptr, A.col, val, x, alpha, beta, y0)
+        assert np.array_equal(y.cpu().numpy(), want), f"{name}: alpha={alpha} beta={beta}"
+    # real-valued: tolerance of the path (1e-12 rel of the row's magnitude in FP64, 2e-5 in FP32)
+    val, x = M.values(A.nnz, A.n, "real", dt)
+    h2, _keep2 = _handle(torch, A, val, x, sigma)
+    y0r = rng.random(A.m).astype(dt)
+    y = torch.from_numpy(y0r.copy()).cuda()
+    assert h2.spmv_axpby(1.5, -0.25, y) == 0
+    torch.cuda.synchronize()
+    want = oracle.csr_axpby(A.m, A.row_ptr, A.col, val, x, 1.5, -0.25, y0r)
+    scale = np.abs(oracle.csr_axpby(A.m, A.row_ptr, A.col, np.abs(val), np.abs(x), 1.5, 0.25, np.abs(y0r)))
+    tol = 1e-12 if dt == np.float64 else 2e-5
+    assert np.all(np.abs(y.cpu().numpy() - want) <= tol * np.maximum(scale, 1e-300)), name
+    for hh in (h, h2):
+        assert hh.destroy() == 0
+        hh.free()
+
+
+def test_axpby_beta_zero_never_reads_y(torch_cuda, oracle):
+    torch = torch_cuda
+    A = M.example_c1()
+    val, x = M.values(A.nnz, A.n, "int")
+    h, _keep = _handle(torch, A, val, x, -1)
+    y = torch.full((A.m,), float("nan"), device="cuda", dtype=torch.float64)
+    assert h.spmv_axpby(1.0, 0.0, y) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(y.cpu().numpy(), oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x))
+    h.free()
+
+
+# ---- the row-block cut of the SpMV (world = 1: no peers, no barriers) ---------------------------------------
+@pytest.mark.parametrize("name,A,sigma", CASES, ids=IDS)
+def test_allgather_world1_chunks_bit_identical(torch_cuda, oracle, name, A, sigma):
+    from benchmark_spmv_using_csr5_b200 import _lib
+    torch = torch_cuda
+    if A.nnz == 0:
+        pytest.skip("empty matrix")
+    for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        val, x = M.values(A.nnz, A.n, "real", dt)   # real values: the cut must not change a single bit
+        h, _keep = _handle(torch, A, val, x, sigma)
+        y_one = torch.full((A.m,), float("nan"), device="cuda", dtype=tdt)
+        assert h.spmv(1.0, y_one) == 0
+        torch.cuda.synchronize()
+        p = h.info().p
+        # carries of multi-tile rows are added with atomics: only rows fed by more than one carry can differ
+        # in the last bit between runs, so compare with the documented tolerance and bit-exactly on int data
+        for chunks in (1, 2, 3, 7, 64):
+            y = torch.full((A.m,), float("nan"), device="cuda", dtype=tdt)
+            ex = _lib.Csr5Exchange()
+            ex.rank, ex.world = 0, 1
+            ex.y_full[0] = y.data_ptr()
+            ex.row_begin = 0
+            ex.chunks = chunks
+            assert h.spmv_allgather(1.0, 0.0, ex) == 0
+            assert h.exchange_status() == 0
+            assert np.allclose(y.cpu().numpy(), y_one.cpu().numpy(), rtol=1e-13 if dt == np.float64 else 1e-6, atol=0), \
+                f"{name}: chunks={chunks} p={p}"
+        vali, xi = M.values(A.nnz, A.n, "int", dt)
+        h2, _k2 = _handle(torch, A, vali, xi, sigma)
+        y = torch.full((A.m,), float("nan"), device="cuda", dtype=tdt)
+        ex = _lib.Csr5Exchange()
+        ex.rank, ex.world = 0, 1
+        ex.y_full[0] = y.data_ptr()
+        ex.chunks = 5
+        assert h2.spmv_allgather(1.0, 0.0, ex) == 0
+        assert h2.exchange_status() == 0
+        assert np.array_equal(y.cpu().numpy(), oracle.csr_spmv(A.m, A.row_ptr, A.col, vali, xi)), name
+        h.free()
+        h2.free()
+
+
+# ---- the single-process sharded handle, several shards on device 0 --------------------------------------------
+TRANSPORTS = ["ce", "push", "inkernel"]
+
+
+@pytest.mark.parametrize("transport", TRANSPORTS)
+@pytest.mark.parametrize("name,A,sigma", CASES, ids=IDS)
+def test_native_sharded_on_one_gpu(torch_cuda, oracle, name, A, sigma, transport):
+    from benchmark_spmv_using_csr5_b200 import sharded as S
+    if A.nnz == 0:
+        pytest.skip("empty matrix")
+    for dt in (np.float64, np.float32):
+        val, x = M.values(A.nnz, A.n, "int", dt)
+        y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+        for shards in (2, 3):
+            sh = S.ShardedCsr5Native([0] * shards, dt)
+            sh.inputCSR(A.m, A.n, A.row_ptr, A.col, val)
+            assert np.array_equal(sh.bounds(), S.row_partition(A.row_ptr, shards)), "C++ and Python partition rules differ"
+            sh.setSigma(sigma)
+            sh.set_exchange(transport, chunks=3, push_ctas=4, barrier=S.BARRIER_EVENTS, timeout_ms=5000)
+            sh.setX(x)
+            sh.asCSR5()
+            for _ in range(3):   # repeated steps alternate the two y buffers and stay exact
+                sh.spmv(1.0)
+            for g in range(shards):
+                assert np.array_equal(sh.y(g), y_ref), f"{name} {dt.__name__} shards={shards} shard {g}"
+            if transport != "inkernel":
+                y_prev = sh.y(0)
+                sh.spmv(2.0, -1.0)   # beta refers to the previous step's y
+                for g in range(shards):
+                    assert np.array_equal(sh.y(g), 2.0 * y_ref - y_prev), f"{name}: beta step, shard {g}"
+            sh.destroy()
+
+
+def test_native_sharded_iterate_feeds_y_back_as_x(torch_cuda, oracle):
+    from benchmark_spmv_using_csr5_b200 import sharded as S
+    A = M.banded(3000, 16)
+    rng = np.random.default_rng(3)
+    val = rng.integers(0, 3, size=A.nnz).astype(np.float64)   # small integers: three steps stay exact in FP64
+    x = rng.integers(0, 3, size=A.n).astype(np.float64)
+    want = x
+    for _ in range(3):
+        want = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, want)
+    for transport in ("ce", "push"):
+        sh = S.ShardedCsr5Native([0, 0, 0], np.float64)
+        sh.inputCSR(A.m, A.n, A.row_ptr, A.col, val)
+        sh.set_exchange(transport, chunks=4, barrier=S.BARRIER_EVENTS, timeout_ms=5000)
+        sh.setX(x)
+        sh.asCSR5()
+        sh.iterate(3)
+        for g in range(3):
+            assert np.array_equal(sh.y(g), want), transport
+        sh.destroy()
+
+
+def test_flag_barriers_two_shards_one_gpu():
+    """The device-side flag barrier (what the multi-process mode uses between GPUs) with two shards on device 0.
+    Run in a child process with enough hardware queues that the two shards' streams never alias (a spinning
+    barrier kernel must not sit in front of the kernel it waits for); the barrier's own time-out turns any
+    such stall into an error instead of a hang."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import oracle
+from benchmark_spmv_using_csr5_b200 import matrices as M, sharded as S
+A = M.example_c1()
+val, x = M.values(A.nnz, A.n, "int", np.float64)
+y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+for transport in ("push", "ce"):
+    sh = S.ShardedCsr5Native([0, 0], np.float64)
+    sh.inputCSR(A.m, A.n, A.row_ptr, A.col, val)
+    sh.set_exchange(transport, chunks=2, push_ctas=2, barrier=S.BARRIER_FLAGS, timeout_ms=4000)
+    sh.setX(x); sh.asCSR5()
+    for _ in range(4):
+        sh.spmv(1.0)
+    sh.synchronize()
+    assert np.array_equal(sh.y(0), y_ref) and np.array_equal(sh.y(1), y_ref), transport
+    sh.destroy()
+print("FLAGS OK")
+''' % ROOT
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0 and "FLAGS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_native_sharded_argument_errors(torch_cuda):
+    from benchmark_spmv_using_csr5_b200 import _lib
+    import ctypes as C
+    lib = _lib.load_library()
+    s = C.c_void_p()
+    assert lib.csr5b200_sharded_create(0, (C.c_int * 1)(0), 8, C.byref(s)) == -101
+    assert lib.csr5b200_sharded_create(1, (C.c_int * 1)(99), 8, C.byref(s)) == -101
+    assert lib.csr5b200_sharded_create(1, (C.c_int * 1)(0), 2, C.byref(s)) == -5
+    assert lib.csr5b200_sharded_create(1, (C.c_int * 1)(0), 8, C.byref(s)) == 0
+    assert lib.csr5b200_sharded_spmv(s, 1.0, 0.0) == -101          # no matrix yet
+    assert lib.csr5b200_sharded_set_exchange(s, 3, 0, 0, 0, 0) == -101   # multicast: multi-process binding only
+    assert lib.csr5b200_sharded_destroy(s) == 0

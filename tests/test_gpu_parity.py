@@ -399,3 +399,124 @@ def test_random_shapes_all_kernels(torch_cuda, oracle):
             y = _spmv(torch, h, A.m, tdt)
             assert np.array_equal(y, y_ref), (trial, kernel, sigma, m, n)
             h.free()
+
+
+# ---- round 2: real-valued full-size parity, the reference's AVX2 path directly, C5 on one GPU -----------------
+
+def _row_sums_fp64(torch, rp, ci, v, x):
+    """Per-row FP64 sums and their magnitudes by an independent route (index_add_ of the products onto their row)."""
+    m = rp.numel() - 1
+    counts = (rp[1:] - rp[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(m, device=rp.device), counts)
+    prod = v.double() * x.double()[ci.long()]
+    ref = torch.zeros(m, device=rp.device, dtype=torch.float64).index_add_(0, rows, prod)
+    mag = torch.zeros(m, device=rp.device, dtype=torch.float64).index_add_(0, rows, prod.abs_())
+    return ref, mag
+
+
+def _full_size_real_check(torch, rp, ci, v, x, dtype, tol, kernels=(1,)):
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    m, n, nnz = rp.numel() - 1, x.numel(), ci.numel()
+    ref, mag = _row_sums_fp64(torch, rp, ci, v, x)
+    for kernel in kernels:
+        h = H.anonymouslibHandle(m, n, dtype)
+        assert h.inputCSR(nnz, rp, ci, v) == 0
+        h.setX(x)
+        h.setSigma(-1)
+        h.set_option(H.OPT_KERNEL, _OPT_KERNEL[kernel])
+        h.set_option(H.OPT_HOT_COLUMNS, _OPT_HOT[kernel])
+        assert h.asCSR5() == 0
+        y = torch.full((m,), float("nan"), device="cuda", dtype=dtype)
+        assert h.spmv(1.0, y) == 0
+        err = ((y.double() - ref).abs() / mag.clamp_min(1e-300)).max().item()
+        assert err <= tol, f"kernel {kernel}: max row-wise relative error {err} > {tol}"
+        assert h.destroy() == 0
+        h.free()
+
+
+def test_full_size_c2_real_valued(torch_cuda):
+    """configs[1] with uniform (0,1] values (bench.py's inputs): every row within 1e-12 of the FP64 row sum
+    (north_star bar: 1e-6)."""
+    torch = torch_cuda
+    m = 10_000_000
+    rp, ci = M.device_banded(m, 16)
+    v, x = M.device_values(ci.numel(), m, "real", torch.float64, "cuda")
+    _full_size_real_check(torch, rp, ci, v, x, torch.float64, FP64_RTOL, kernels=(1, 5))
+
+
+def test_full_size_c3_real_valued(torch_cuda):
+    """configs[2] with uniform (0,1] values: hub rows of ~1e5 terms, carries through hundreds of tiles."""
+    torch = torch_cuda
+    rp, ci = M.device_rmat(22)
+    n = rp.numel() - 1
+    v, x = M.device_values(ci.numel(), n, "real", torch.float64, "cuda")
+    _full_size_real_check(torch, rp, ci, v, x, torch.float64, FP64_RTOL, kernels=(1, 3))
+
+
+def test_full_size_c5_rmat25_one_gpu(torch_cuda):
+    """configs[4]'s matrix (R-MAT scale 25, ~5.2e8 nnz, 6.9 GB) on ONE GPU: bit-exact on integer-valued inputs
+    against exact segment sums, and the asCSR5 -> asCSR round trip at that size (33.5 M rows, 57 % of them empty)."""
+    torch = torch_cuda
+    rp, ci = M.device_rmat(25)
+    n = rp.numel() - 1
+    v, x = M.device_values(ci.numel(), n, "int", torch.float64, "cuda")
+    _full_size_check(torch, rp, ci, v, x, torch.float64, kernels=(1,))
+    del v, x
+    torch.cuda.empty_cache()
+    v, x = M.device_values(ci.numel(), n, "real", torch.float64, "cuda")
+    _full_size_real_check(torch, rp, ci, v, x, torch.float64, FP64_RTOL)
+
+
+def test_cuda_y_vs_reference_avx2_directly(torch_cuda, oracle):
+    """north_star: 'results match the reference AVX2 path's y within 1e-6 relative on FP64' -- the CUDA y against
+    the y of the reference's own CSR5_avx2 (compiled from /root/reference into oracle/_ref), no oracle in between."""
+    torch = torch_cuda
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libref_avx2.so not built (needs /root/reference at build time)")
+    shapes = [("banded_300k", M.banded(300_000, 16)), ("rmat16", M.rmat(16)), ("example_c1", M.example_c1()),
+              ("lap27_40", M.laplacian27(40)[0])]
+    for name, A in shapes:
+        for kind, tol in (("int", 0.0), ("real", 1e-6)):
+            val, x = M.values(A.nnz, A.n, kind)
+            y_avx2 = oracle.ref_avx2_spmv(A.m, A.n, A.row_ptr, A.col, val, x)
+            h, _keep = _handle(torch, A, val, x, -1, kernel=1)
+            y = _spmv(torch, h, A.m, torch.float64)
+            if kind == "int":
+                assert np.array_equal(y, y_avx2), name
+            else:
+                denom = np.maximum(np.abs(y_avx2), 1e-300)
+                worst = float(np.max(np.abs(y - y_avx2) / denom))
+                assert worst <= tol, f"{name}: {worst}"
+                assert worst <= 1e-12, f"{name}: {worst} (expected ~1e-15)"
+            h.free()
+
+
+def test_sigma_rule_b200_is_bit_exact_too(torch_cuda, oracle):
+    """CSR5B200_OPT_SIGMA_RULE: the reference's table stays the default (metadata word for word); the rule measured
+    on B200 only changes which sigma AUTO picks -- both are bit-exact against the oracle run at the same sigma."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    for name, A, _sigma in CASES:
+        if A.nnz == 0:
+            continue
+        for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+            val, x = M.values(A.nnz, A.n, "int", dt)
+            y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+            for rule in (H.SIGMA_RULE_REFERENCE, H.SIGMA_RULE_B200):
+                rp, ci, v, xd = _upload(torch, A, val, x)
+                h = H.anonymouslibHandle(A.m, A.n, tdt)
+                assert h.inputCSR(A.nnz, rp, ci, v) == 0
+                h.setX(xd)
+                assert h.set_option(H.OPT_SIGMA_RULE, rule) == 0
+                h.setSigma(H.ANONYMOUSLIB_AUTO_TUNED_SIGMA)
+                assert h.asCSR5() == 0
+                s = h.info().sigma
+                if rule == H.SIGMA_RULE_REFERENCE:
+                    assert s == oracle.auto_sigma(A.m, A.nnz), name
+                assert 4 <= s <= 32
+                y = _spmv(torch, h, A.m, tdt)
+                assert np.array_equal(y, y_ref), (name, rule, s)
+                assert np.array_equal(y, oracle.csr5_spmv(A.m, A.n, A.row_ptr, A.col, val, x, s)), (name, rule, s)
+                got, want = h.meta_to_host(), oracle.csr5_meta(A.m, A.nnz, s, A.row_ptr)
+                assert np.array_equal(got["tile_ptr"], want.tile_ptr) and np.array_equal(got["desc"], want.desc)
+                h.free()

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "csr5_b200.h")).read()
+    src = "".join(open(h).read() for h in _lib.HEADER_PATHS)   # csr5_b200.h + csr5_b200_sharded.h
     return sorted(set(re.findall(r"CSR5B200_API\s+[\w\s\*]+?\b(csr5b200_\w+)\s*\(", src)))
 
 
@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported_and_typed():
     declared = _declared_symbols()
     assert len(declared) >= 18
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/csr5_b200.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.SIGNATURES"
     assert sorted(_lib.SIGNATURES) == declared
 
@@ -87,8 +87,8 @@ def test_header_is_plain_c_and_links(tmp_path):
     import subprocess
     gcc = shutil.which("gcc") or "/usr/bin/gcc"
     src = tmp_path / "t.c"
-    src.write_text('#include <stdio.h>\n#include "csr5_b200.h"\n'
-                   'int main(void) { csr5b200_handle_t h = 0; csr5b200_info info;\n'
+    src.write_text('#include <stdio.h>\n#include "csr5_b200.h"\n#include "csr5_b200_sharded.h"\n'
+                   'int main(void) { csr5b200_handle_t h = 0; csr5b200_info info; csr5b200_exchange ex; (void)ex;\n'
                    '  if (csr5b200_create(3, 4, 8, &h)) return 1;\n'
                    '  if (csr5b200_get_info(h, &info) || info.m != 3 || info.n != 4) return 2;\n'
                    '  if (csr5b200_spmv(h, 1.0, (void *)16) != CSR5B200_UNKNOWN_FORMAT) return 3;\n'

@@ -1,0 +1,63 @@
+#!/bin/bash
+# One parametrised GPU-box script (replaces the per-experiment scripts of round 1).  Usage, under gpurun:
+#   bash tools/gpu/run.sh <stage> [<stage> ...]
+# Stages write into gpurun_out/ (merged back by gpurun); each runs under its own timeout so that a hang costs
+# minutes, not the box.  TAG (env, default r02) prefixes the output files.
+#   tests            python -m pytest tests -m gpu
+#   smoke            __graft_entry__.smoke()
+#   bench            python bench.py (defaults) -> ${TAG}_bench_c2.json
+#   bench:<args>     python bench.py <args with ',' for ' '> -> ${TAG}_bench_<args>.json
+#   mbench:<N>:<args> torchrun, N ranks
+#   probe[:c3,c5]    tools/gpu/probe.py (gather floor microbenchmarks, hot-table variants, conversion phases)
+#   sigma            tools/gpu/sweep_sigma.py (sigma rule sweep)
+#   launches:<wl>    ncu launch list of one bench run of workload <wl>
+#   ncu:<wl>:<regex>[:<bench args>] ncu --set full of the kernels matching <regex>
+#   mtests:<N>       tests/multigpu_worker.py on N ranks
+set -u
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+TAG=${TAG:-r02}
+export CUDA_DEVICE_MAX_CONNECTIONS=32
+PORT=29517
+for stage in "$@"; do
+  name=${stage%%:*}; rest=${stage#*:}; [ "$rest" == "$stage" ] && rest=""
+  echo "=== stage $stage ($(date +%T))"
+  case $name in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q ${rest//,/ } 2>&1 | tail -25 | tee gpurun_out/${TAG}_tests.txt ;;
+    smoke)
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/${TAG}_smoke.txt ;;
+    bench)
+      args=${rest//,/ }; label=$(echo "${rest:-c2}" | tr -c 'A-Za-z0-9\n' '_')
+      timeout 1200 python bench.py $args > gpurun_out/${TAG}_bench_${label}.json 2> gpurun_out/${TAG}_bench_${label}.log
+      echo "rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_${label}.json; tail -3 gpurun_out/${TAG}_bench_${label}.log ;;
+    mbench)
+      n=${rest%%:*}; a=${rest#*:}; [ "$a" == "$rest" ] && a=""
+      args=${a//,/ }; label=$(echo "n${n}_${a}" | tr -c 'A-Za-z0-9\n' '_')
+      PORT=$((PORT+1))
+      timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $PORT \
+        bench.py --gpus $n $args > gpurun_out/${TAG}_bench_${label}.json 2> gpurun_out/${TAG}_bench_${label}.log
+      echo "rc=$?"; tail -c 3000 gpurun_out/${TAG}_bench_${label}.json; grep -v "^W\|^\*\*\*" gpurun_out/${TAG}_bench_${label}.log | tail -8 ;;
+    mtests)
+      PORT=$((PORT+1))
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${rest:-2} --master-addr 127.0.0.1 --master-port $PORT \
+        tests/multigpu_worker.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -12 | tee gpurun_out/${TAG}_mtests_n${rest:-2}.txt ;;
+    probe)
+      timeout 1500 python tools/gpu/probe.py ${rest:-c3,c5,c2} 2>&1 | tee gpurun_out/${TAG}_probe.txt | tail -60 ;;
+    sigma)
+      timeout 1500 python tools/gpu/sweep_sigma.py 2>&1 | tee gpurun_out/${TAG}_sweep_sigma.txt | tail -40 ;;
+    launches)
+      wl=${rest:-c2}
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_${wl}.csv \
+        python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/${TAG}_launches_${wl}.log 2>&1
+      echo "rc=$?"; tail -3 gpurun_out/${TAG}_launches_${wl}.csv ;;
+    ncu)
+      wl=${rest%%:*}; r2=${rest#*:}; rx=${r2%%:*}; extra=${r2#*:}; [ "$extra" == "$r2" ] && extra=""
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$rx -s 10 -c 2 -f -o gpurun_out/${TAG}_ncu_${wl}_${rx} \
+        python bench.py --workload $wl --steps 12 --warmup 3 --no-cpu-baseline --no-e2e --no-extra ${extra//,/ } > gpurun_out/${TAG}_ncu_${wl}_${rx}.log 2>&1
+      echo "rc=$?"; ls -la gpurun_out/${TAG}_ncu_${wl}_${rx}.ncu-rep ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${TAG}_nvidia_smi.csv 2>&1
+echo "=== done ($(date +%T))"

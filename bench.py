@@ -381,8 +381,8 @@ def measure_single(torch, H, name, args, device, windows, steps, full):
     A = H.anonymouslibHandle(m, n, dtype)
     assert A.inputCSR(nnz, w["row_ptr"], w["col"], w["val"]) == 0
     assert A.setX(w["x"]) == 0
+    apply_tuning(A, H, args)   # before setSigma: the rule behind AUTO is one of the options
     A.setSigma(args.sigma)
-    apply_tuning(A, H, args)
     A.warmup()
     torch.cuda.synchronize()
     conv = []
@@ -516,6 +516,7 @@ def main_single(args, torch, H, device):
         "dtype": "f64" if vb == 8 else "f32", "data": "synthetic",
         "config": {
             "workload": WORKLOADS[args.workload], "m": r["m"], "n": r["n"], "nnz": r["nnz"], "sigma": i.sigma,
+            "sigma_rule": "reference table (anonymouslib_cuda.h:297-313)" if args.sigma_rule == 0 else "measured on B200 (CSR5B200_OPT_SIGMA_RULE = 1)",
             "omega": 32, "tiles_per_gpu": i.p, "num_packet": i.num_packet, "values": "uniform (0,1], seed 42",
             "l2": f"inputs larger than L2 ({b_alg / 1e6:.0f} MB streamed per step vs 126 MB L2); no flush needed",
             "kernel": r["roofline"]["kernel"], "launches_per_step": r["launches"],
@@ -549,7 +550,7 @@ def gather_rows(torch, dist, local, bounds, rank, device):
 
 
 def make_sharded(S, w, n, args, exch, transport=None, chunks=None, push_ctas=None):
-    kw = dict(sigma=args.sigma)
+    kw = dict(sigma=args.sigma, sigma_rule=args.sigma_rule)
     if exch == "nccl":
         return S.ShardedCsr5(w["bounds"], n, w["row_ptr"], w["col"], w["val"], mode="nccl", **kw)
     if exch in ("fused", "fused-unicast"):
@@ -834,7 +835,9 @@ def main_multi(args, torch, H, device, rank, world, local_rank):
         "config": {
             "workload": WORKLOADS[args.workload] + (f"; rank g owns rows [bounds[g], bounds[g+1]) of the {r['m_total']}-row "
                                                     f"matrix, x replicated, y concatenated on every rank each step ({r['multi']['exchange']})"),
-            "m": r["m_total"], "n": r["n"], "nnz": r["total_nnz"], "sigma": i.sigma, "omega": 32, "tiles_per_gpu": i.p,
+            "m": r["m_total"], "n": r["n"], "nnz": r["total_nnz"], "sigma": i.sigma,
+            "sigma_rule": "reference table (anonymouslib_cuda.h:297-313)" if args.sigma_rule == 0 else "measured on B200 (CSR5B200_OPT_SIGMA_RULE = 1)",
+            "omega": 32, "tiles_per_gpu": i.p,
             "num_packet": i.num_packet, "values": "uniform (0,1], seed 42",
             "l2": f"inputs larger than L2 ({b_alg / 1e6:.0f} MB streamed per GPU per step vs 126 MB L2); no flush needed",
             "kernel": roofline["kernel"], "launches_per_step": r["launches"],
@@ -865,7 +868,7 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--sigma", type=int, default=-1)
-    ap.add_argument("--sigma-rule", type=int, default=0, help="0 = the reference's table (anonymouslib_cuda.h:297-313), 1 = the rule measured on B200")
+    ap.add_argument("--sigma-rule", type=int, default=1, help="0 = the reference's table (anonymouslib_cuda.h:297-313), 1 = the rule measured on B200")
     ap.add_argument("--hot", type=int, default=0, help="hot-column table: 0 off (default), -1 auto, K entries")
     ap.add_argument("--hot-threads", type=int, default=0)
     ap.add_argument("--wpb", type=int, default=0, help="tuning: warps per CTA of the direct kernel")

@@ -4,6 +4,7 @@
 // col/val are permuted in place between asCSR5() and asCSR().
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -92,16 +93,24 @@ int auto_sigma(int m, int nnz)
     return 6;
 }
 
-// CSR5B200_OPT_SIGMA_RULE = 1: the table measured on B200 (profiles/r02_sigma_rule.md), replacing the reference's
-// Maxwell-era one above.  Same input (k = nnz / m) so that it stays a drop-in for setSigma(AUTO).
+// CSR5B200_OPT_SIGMA_RULE = 1: the table measured on B200 (profiles/r02_sigma_rule.md; sweep of nnz/row 2..300 x
+// {FP64, FP32} x sigma 4..32, tools/gpu/sweep_sigma.py), replacing the reference's Maxwell-era one above.  Same input
+// (k = nnz / m) so that it stays a drop-in for setSigma(AUTO).  What the sweep shows: tiles of a few hundred bytes
+// (sigma = k for short rows) cost 10-30 %; FP64 tiles whose val slab is a power of two in bytes (sigma 8, 16, 32:
+// 2 / 4 / 8 KB strides between concurrently streaming warps) lose 4-6 % to their neighbours; beyond that the curve
+// is flat within 1-3 %.
 int auto_sigma_b200(int m, int nnz, int value_bytes)
 {
     const int k = m > 0 ? nnz / m : 0;
-    (void)value_bytes;
-    if (k <= 4) return 4;
-    if (k <= 32) return k;
-    if (k <= 256) return 32;
-    return 6;
+    if (value_bytes == 8) {
+        if (k <= 2) return 4;
+        if (k <= 5) return 12;
+        return 14;
+    }
+    if (k <= 2) return 8;
+    if (k == 3) return 12;
+    if (k <= 22) return 16;
+    return 24;
 }
 
 // Hot-column table: pick the most referenced columns of the CSR5 tiles, at most
@@ -187,6 +196,9 @@ int csr5b200_create(int m, int n, int value_bytes, csr5b200_handle_t *out)
     if (cudaGetDevice(&dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
         h->tune.num_sms = sms;
+    // opt-in for unmodified callers of the reference API (the shim only ever calls setSigma(AUTO))
+    const char *rule = std::getenv("CSR5B200_SIGMA_RULE");
+    if (rule && (!std::strcmp(rule, "b200") || !std::strcmp(rule, "1"))) h->sigma_rule = 1;
     *out = h;
     return CSR5B200_SUCCESS;
 }

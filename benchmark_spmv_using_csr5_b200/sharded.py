@@ -104,7 +104,7 @@ class ShardedCsr5:
 
     def __init__(self, bounds, n: int, local_row_ptr, col, val, group=None, mode: str = "overlap",
                  sigma: int = -1, multicast: bool | None = None, scheme: int = 0, transport: str | int = "auto",
-                 chunks: int = 0, push_ctas: int = 0, timeout_ms: int = 0):
+                 chunks: int = 0, push_ctas: int = 0, timeout_ms: int = 0, sigma_rule: int = 0):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -130,6 +130,7 @@ class ShardedCsr5:
         err = self.h.inputCSR(int(col.numel()), local_row_ptr, col, val)
         if err:
             raise RuntimeError(self.h.error_string(err))
+        self.h.set_option(H.OPT_SIGMA_RULE, int(sigma_rule))
         self.h.setSigma(sigma)
         self.scheme = int(scheme)   # fused mode: 0 auto, 1 stores fused into the SpMV kernels, 2 coalesced push pass
         self.transport = H.TRANSPORT_NAMES[transport] if isinstance(transport, str) else int(transport)

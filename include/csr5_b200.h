@@ -185,7 +185,8 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
                                          all destinations), 2 push (one coalesced copy pass after the SpMV) */
 #define CSR5B200_OPT_SIGMA_RULE    12 /* what CSR5B200_AUTO_TUNED_SIGMA means at the next set_sigma(): 0 (default) the reference's
                                          table r/s/t/u = 4/32/256/6 (anonymouslib_cuda.h:297-313; keeps the CSR5 arrays word for
-                                         word those of the reference), 1 the rule measured on B200 (profiles/r02_sigma_rule.md) */
+                                         word those of the reference), 1 the rule measured on B200 (profiles/r02_sigma_rule.md); the environment variable
+                                         CSR5B200_SIGMA_RULE=b200 sets it for every handle of an unmodified caller */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays

@@ -651,9 +651,9 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
 
     variants = {}
     if args.sweep_exchange and exch == "overlap":
-        for spec in args.sweep_exchange.split(","):
-            tr, _, rest = spec.partition(":")
-            ch, _, ctas = rest.partition(":")
+        for spec in args.sweep_exchange.split("+"):
+            tr, _, rest = spec.partition("/")
+            ch, _, ctas = rest.partition("/")
             if tr == "multicast" and not sh.has_multicast:
                 variants[spec] = "no multicast address"
                 continue
@@ -879,7 +879,7 @@ def main():
     ap.add_argument("--transport", default="auto", choices=["auto", "ce", "push", "multicast", "inkernel", "none"])
     ap.add_argument("--chunks", type=int, default=0, help="overlap: row blocks per step (0 = default)")
     ap.add_argument("--push-ctas", type=int, default=0, help="overlap, SM transports: CTAs of the push grid (0 = default)")
-    ap.add_argument("--sweep-exchange", default="", help="overlap: also time these variants, e.g. 'ce:8,push:8:32,multicast:8:32'")
+    ap.add_argument("--sweep-exchange", default="", help="overlap: also time these variants, e.g. 'ce/8+push/8/32+multicast/8/32' (transport/chunks/push CTAs)")
     ap.add_argument("--scheme", type=int, default=0, help="fused modes: 0 auto, 1 in-kernel stores, 2 push pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

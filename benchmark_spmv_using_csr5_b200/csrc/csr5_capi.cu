@@ -433,7 +433,7 @@ static int spmv_impl(csr5b200_handle_t h, double alpha, double beta, void *y, in
         int exchange = s.exchange;
         if (exchange == 0)
             exchange = (!h->pl.needs_zero_fill && h->pl.m > 0 && (long long)h->pl.nnz / h->pl.m <= 64) ? 1 : 2;
-        if (exchange == 1 && !multicast) {
+        if (exchange == 1 && !multicast && h->pl.m > 0) {
             bool has_local = false;
             for (int k = 0; k < n_dst; k++) has_local |= y_dst[k] == y;
             if (!has_local) return CSR5B200_INVALID_ARGUMENT;

@@ -9,12 +9,18 @@
 //   side              [entry barrier]  [carry 0][ship 0] [carry 1][ship 1] ...
 //   ce[k] (k != rank) .                        [copy 0 -> k]      [copy 1 -> k] ...     (COPY_ENGINE transport only)
 //
-// Row blocks are independent (a row is stored once, by the tile in which it starts; a block's carry pass only
-// touches rows that started in it or earlier), so consecutive blocks go to two alternating streams and overlap
-// at their edges -- no partial-wave bubble per block.  After block c and its carry pass, every row below the row
-// that holds the first non-zero of block c + 1 is final and can leave.
+// Row blocks are independent of each other and of their order: a row is stored once, by the tile in which it starts;
+// a block's carry pass adds the carries of its own tiles EXCEPT those into the one row that crossed in from an earlier
+// block.  After block c and its carry pass every row that lies inside the block is final and leaves; the (at most
+// one per block) crossing rows get their held-back carries in one boundary pass after the last block and leave
+// last.  Consecutive blocks go to two alternating streams and overlap at their edges -- no partial-wave bubble per
+// block -- and the blocks run ship-heavy first (most rows per tile: a power-law shard keeps its millions of short
+// and empty rows at the end), the order that minimises the makespan of the two-stage compute -> ship pipeline.
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
+#include <numeric>
 
 #include "csr5_handle.h"
 
@@ -79,6 +85,16 @@ cudaError_t launch_flag_barrier(uint32_t *const *flags, int rank, int world, int
 cudaError_t launch_push_rows_f64(const void *, void *const *, int, int, long long, int, cudaStream_t);
 cudaError_t launch_push_rows_f32(const void *, void *const *, int, int, long long, int, cudaStream_t);
 
+cudaError_t launch_push_row_list_f64(const void *, void *const *, int, int, const int *, int, cudaStream_t);
+cudaError_t launch_push_row_list_f32(const void *, void *const *, int, int, const int *, int, cudaStream_t);
+
+cudaError_t launch_push_row_list(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
+                                 const int *rows, int n, cudaStream_t stream)
+{
+    return value_bytes == 8 ? launch_push_row_list_f64(y_local, dst, n_dst, multicast, rows, n, stream)
+                            : launch_push_row_list_f32(y_local, dst, n_dst, multicast, rows, n, stream);
+}
+
 cudaError_t launch_push_rows(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
                              long long rows, int grid, cudaStream_t stream)
 {
@@ -93,10 +109,12 @@ void release_exchange(csr5b200_handle_t h)
     auto de = [](cudaEvent_t &e) { if (e) cudaEventDestroy(e); e = nullptr; };
     ds(x.work1);
     ds(x.side);
+    ds(x.ship);
     for (auto &s : x.ce) ds(s);
     de(x.ev_begin);
     de(x.ev_side_done);
     de(x.ev_work1_done);
+    de(x.ev_ship_done);
     for (auto &e : x.ev_chunk) de(e);
     for (auto &e : x.ev_cal) de(e);
     for (auto &e : x.ev_ce_done) de(e);
@@ -122,11 +140,13 @@ int ensure_state(csr5b200_handle_t h)
     CUX(cudaStreamCreateWithPriority(&x.work1, cudaStreamNonBlocking, lo));
     // the shipping stream outranks the SpMV so that its small kernels get SM slots as soon as CTAs retire
     CUX(cudaStreamCreateWithPriority(&x.side, cudaStreamNonBlocking, hi));
+    CUX(cudaStreamCreateWithPriority(&x.ship, cudaStreamNonBlocking, hi));
     for (auto &s : x.ce) CUX(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
     const unsigned fl = cudaEventDisableTiming;
     CUX(cudaEventCreateWithFlags(&x.ev_begin, fl));
     CUX(cudaEventCreateWithFlags(&x.ev_side_done, fl));
     CUX(cudaEventCreateWithFlags(&x.ev_work1_done, fl));
+    CUX(cudaEventCreateWithFlags(&x.ev_ship_done, fl));
     for (auto &e : x.ev_chunk) CUX(cudaEventCreateWithFlags(&e, fl));
     for (auto &e : x.ev_cal) CUX(cudaEventCreateWithFlags(&e, fl));
     for (auto &e : x.ev_ce_done) CUX(cudaEventCreateWithFlags(&e, fl));
@@ -138,7 +158,8 @@ int ensure_state(csr5b200_handle_t h)
     return CSR5B200_SUCCESS;
 }
 
-// Row-block boundaries: equal tile counts; rows from tile_ptr (one small blocking read-back, cached).
+// Row-block plan (cached): boundaries in tiles, the rows they fall into, which of those rows cross in from the block
+// before, and the order the blocks run in.  Two small blocking read-backs.
 int ensure_chunks(csr5b200_handle_t h, int chunks)
 {
     ExchangeState &x = h->ex;
@@ -150,13 +171,42 @@ int ensure_chunks(csr5b200_handle_t h, int chunks)
     if (x.chunks == chunks && (int)x.chunk_tile.size() == chunks + 1) return CSR5B200_SUCCESS;
     x.chunk_tile.assign(chunks + 1, 0);
     x.chunk_row.assign(chunks + 1, 0);
+    x.chunk_carried.assign(chunks, 0);
     for (int c = 0; c <= chunks; c++) x.chunk_tile[c] = (int)((long long)ntiles * c / chunks);
     x.chunk_row[chunks] = pl.m;
     std::vector<uint32_t> tp(chunks + 1, 0);
-    for (int c = 1; c < chunks; c++)
+    std::vector<int> rp(chunks + 1, 0);
+    for (int c = 0; c < chunks; c++)
         CUX(cudaMemcpyAsync(&tp[c], pl.tile_ptr + x.chunk_tile[c], sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CUX(cudaStreamSynchronize(h->stream));
-    for (int c = 1; c < chunks; c++) x.chunk_row[c] = (int)(tp[c] & ROW_MASK);
+    for (int c = 0; c < chunks; c++) x.chunk_row[c] = (int)(tp[c] & ROW_MASK);
+    for (int c = 1; c < chunks; c++)
+        CUX(cudaMemcpyAsync(&rp[c], pl.row_ptr + x.chunk_row[c], sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUX(cudaStreamSynchronize(h->stream));
+    const long long tile_nnz = (long long)OMEGA * pl.sigma;
+    x.n_boundary_rows = 0;
+    for (int c = 1; c < chunks; c++) {
+        // row chunk_row[c] holds the first non-zero of block c: it crosses in unless it starts exactly there
+        x.chunk_carried[c] = (long long)rp[c] != x.chunk_tile[c] * tile_nnz;
+        if (x.chunk_tile[c] == x.chunk_tile[c + 1] && c + 1 < chunks) x.chunk_carried[c] = 0;   // empty block
+        if (x.chunk_carried[c] &&
+            (x.n_boundary_rows == 0 || x.boundary_rows[x.n_boundary_rows - 1] != x.chunk_row[c]))
+            x.boundary_rows[x.n_boundary_rows++] = x.chunk_row[c];
+    }
+    x.chunk_row[0] = 0;   // leading empty rows belong to the first block (cleared by the prologue)
+    x.table = ChunkTable();
+    x.table.n = chunks;
+    for (int c = 0; c <= chunks; c++) x.table.tile_begin[c] = x.chunk_tile[c];
+    for (int c = 0; c < chunks; c++) x.table.skip_row[c] = x.chunk_carried[c] ? x.chunk_row[c] : -1;
+    // Order: ship-heavy blocks first (Johnson's rule for a two-stage pipeline whose first stage -- the SpMV of a block --
+    // costs about the same for every block); uniform matrices keep the natural order.
+    x.chunk_order.resize(chunks);
+    std::iota(x.chunk_order.begin(), x.chunk_order.end(), 0);
+    auto rows_of = [&](int c) { return (long long)x.chunk_row[c + 1] - x.chunk_row[c]; };
+    long long lo = rows_of(0), hi = rows_of(0);
+    for (int c = 1; c < chunks; c++) { lo = std::min(lo, rows_of(c)); hi = std::max(hi, rows_of(c)); }
+    if (hi > 2 * lo + 1024)
+        std::stable_sort(x.chunk_order.begin(), x.chunk_order.end(), [&](int a, int b) { return rows_of(a) > rows_of(b); });
     x.chunks = chunks;
     return CSR5B200_SUCCESS;
 }
@@ -196,7 +246,15 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         if (!ex->flags[k]) barriers = false;
     int transport = ex->transport;
     if (transport < 0 || transport > CSR5B200_TRANSPORT_NONE) return CSR5B200_INVALID_ARGUMENT;
-    if (transport == CSR5B200_TRANSPORT_AUTO) transport = CSR5B200_TRANSPORT_COPY_ENGINE;
+    if (transport == CSR5B200_TRANSPORT_AUTO) {
+        // measured on 2 and 8 B200 (profiles/r02_bench_c2_n2_sweep*.json, ..._n8_sweep*.json): from 3 GPUs up the
+        // NVSwitch multicast address wins by a wide margin (one store per row instead of N - 1, whatever the rows
+        // per shard), without it the push grid; between 2 GPUs the copy engine, or -- for matrices whose tiles
+        // store runs of consecutive rows -- the SpMV kernel's own peer stores
+        const bool consecutive = !pl.needs_zero_fill && pl.m > 0 && (long long)pl.nnz / pl.m <= 64;
+        if (world >= 3) transport = ex->y_multicast ? CSR5B200_TRANSPORT_SM_MULTICAST : CSR5B200_TRANSPORT_SM_PUSH;
+        else transport = (consecutive && beta == 0.0) ? CSR5B200_TRANSPORT_IN_KERNEL : CSR5B200_TRANSPORT_COPY_ENGINE;
+    }
     if (transport == CSR5B200_TRANSPORT_SM_MULTICAST && !ex->y_multicast) return CSR5B200_INVALID_ARGUMENT;
     if (world == 1) transport = CSR5B200_TRANSPORT_NONE;
     if (transport == CSR5B200_TRANSPORT_IN_KERNEL && beta != 0.0) return CSR5B200_INVALID_ARGUMENT;
@@ -231,11 +289,11 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         return CSR5B200_SUCCESS;
     }
 
-    int chunks = ex->chunks > 0 ? ex->chunks : 8;
-    if (transport == CSR5B200_TRANSPORT_IN_KERNEL || transport == CSR5B200_TRANSPORT_NONE) chunks = 1;
+    int chunks = ex->chunks > 0 ? ex->chunks : 12;
+    if (transport == CSR5B200_TRANSPORT_IN_KERNEL) chunks = 1;
     if ((err = ensure_chunks(h, chunks))) return err;
     chunks = x.chunks;
-    const int push_ctas = ex->push_ctas > 0 ? ex->push_ctas : 32;
+    const int push_ctas = ex->push_ctas > 0 ? ex->push_ctas : 48;
 
     if (!x.warmed) {
         // Load every module of the step now: CUDA loads kernels lazily at their first launch, and that load
@@ -285,22 +343,31 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         pro.tiles = pro.calibrate = false;
         CUX(spmv_part(h, alpha, beta, y_local, nullptr, pro, S));
     }
+    const bool ship = transport != CSR5B200_TRANSPORT_NONE;
+    const bool by_ce = transport == CSR5B200_TRANSPORT_COPY_ENGINE;
+    const bool by_mc = transport == CSR5B200_TRANSPORT_SM_MULTICAST;
     CUX(cudaEventRecord(x.ev_begin, S));
     CUX(cudaStreamWaitEvent(x.side, x.ev_begin, 0));
     if (chunks > 1) CUX(cudaStreamWaitEvent(x.work1, x.ev_begin, 0));
-    const bool ship = transport != CSR5B200_TRANSPORT_NONE;
     if (barriers && ex->entry_barrier && ship) {
         CUX(launch_flag_barrier(ex->flags, rank, world, 0, x.epoch, x.status, ex->timeout_ms, x.side));
         ++h->launches_per_spmv;
     }
-    if (ship && transport == CSR5B200_TRANSPORT_COPY_ENGINE)
-        for (int k = 0; k < world; k++)
-            if (k != rank) CUX(cudaStreamWaitEvent(x.ce[k], x.ev_begin, 0));
 
-    void *dst[CSR5B200_MAX_SCATTER] = {};
+    // destinations of the SM transports, relative to this shard's first row
+    void *dst0[CSR5B200_MAX_SCATTER] = {};
     int n_dst = 0;
-    for (int c = 0; c < chunks; c++) {
-        cudaStream_t W = (c & 1) ? x.work1 : S;
+    const size_t seg = (size_t)ex->row_begin * vb;
+    if (by_mc) {
+        dst0[n_dst++] = static_cast<char *>(ex->y_multicast) + seg;
+    } else {
+        for (int k = 0; k < world; k++)
+            if (k != rank) dst0[n_dst++] = static_cast<char *>(ex->y_full[k]) + seg;
+    }
+
+    for (int i = 0; i < chunks; i++) {
+        const int c = x.chunk_order[i];
+        cudaStream_t W = (i & 1) ? x.work1 : S;
         SpmvCall blk;
         blk.tile_begin = x.chunk_tile[c];
         blk.tile_end = x.chunk_tile[c + 1];
@@ -308,55 +375,62 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         blk.prologue = false;
         blk.calibrate = false;
         CUX(spmv_part(h, alpha, beta, y_local, nullptr, blk, W));
-        CUX(cudaEventRecord(x.ev_chunk[c], W));
+        CUX(cudaEventRecord(x.ev_chunk[i], W));
 
-        // carry pass of the block, then its finished rows leave
-        CUX(cudaStreamWaitEvent(x.side, x.ev_chunk[c], 0));
+        // carry pass of the block (all but the carries into the row that crossed in), then its rows leave
+        CUX(cudaStreamWaitEvent(x.side, x.ev_chunk[i], 0));
         SpmvCall cal = blk;
         cal.tiles = false;
         cal.calibrate = true;
+        cal.skip_row = x.table.skip_row[c];
         CUX(spmv_part(h, alpha, beta, y_local, nullptr, cal, x.side));
-        const long long ra = x.chunk_row[c], rb = x.chunk_row[c + 1];
+        const long long ra = (long long)x.chunk_row[c] + (x.chunk_carried[c] ? 1 : 0), rb = x.chunk_row[c + 1];
         if (!ship || rb <= ra) continue;
+        CUX(cudaEventRecord(x.ev_cal[i], x.side));
         const char *src = y_local + (size_t)ra * vb;
-        const size_t off = ((size_t)ex->row_begin + (size_t)ra) * vb;
-        if (transport == CSR5B200_TRANSPORT_COPY_ENGINE) {
-            CUX(cudaEventRecord(x.ev_cal[c], x.side));
+        if (by_ce) {
             for (int k = 0; k < world; k++) {
                 if (k == rank) continue;
-                CUX(cudaStreamWaitEvent(x.ce[k], x.ev_cal[c], 0));
-                CUX(cudaMemcpyAsync(static_cast<char *>(ex->y_full[k]) + off, src, (size_t)(rb - ra) * vb,
+                CUX(cudaStreamWaitEvent(x.ce[k], x.ev_cal[i], 0));
+                CUX(cudaMemcpyAsync(static_cast<char *>(ex->y_full[k]) + seg + (size_t)ra * vb, src, (size_t)(rb - ra) * vb,
                                     cudaMemcpyDefault, x.ce[k]));
                 ++h->launches_per_spmv;
             }
         } else {
-            if (transport == CSR5B200_TRANSPORT_SM_MULTICAST) {
-                dst[0] = static_cast<char *>(ex->y_multicast) + off;
-                n_dst = 1;
-            } else {
-                n_dst = 0;
-                for (int k = 0; k < world; k++)
-                    if (k != rank) dst[n_dst++] = static_cast<char *>(ex->y_full[k]) + off;
-            }
-            CUX(launch_push_rows((int)vb, src, dst, n_dst, transport == CSR5B200_TRANSPORT_SM_MULTICAST, rb - ra,
-                                 push_ctas, x.side));
+            void *dst[CSR5B200_MAX_SCATTER] = {};
+            for (int k = 0; k < n_dst; k++) dst[k] = static_cast<char *>(dst0[k]) + (size_t)ra * vb;
+            CUX(cudaStreamWaitEvent(x.ship, x.ev_cal[i], 0));
+            CUX(launch_push_rows((int)vb, src, dst, n_dst, by_mc ? 1 : 0, rb - ra, push_ctas, x.ship));
             ++h->launches_per_spmv;
         }
     }
 
-    // ---- join --------------------------------------------------------------------------------------------------
+    // ---- join: boundary pass, crossing rows, barrier -----------------------------------------------------------
     if (chunks > 1) {
         CUX(cudaEventRecord(x.ev_work1_done, x.work1));
         CUX(cudaStreamWaitEvent(S, x.ev_work1_done, 0));
     }
     CUX(cudaEventRecord(x.ev_side_done, x.side));
     CUX(cudaStreamWaitEvent(S, x.ev_side_done, 0));
-    if (ship && transport == CSR5B200_TRANSPORT_COPY_ENGINE)
+    if (x.n_boundary_rows > 0) {
+        SpmvCall bnd;
+        bnd.boundary = &x.table;
+        CUX(spmv_part(h, alpha, beta, y_local, nullptr, bnd, S));
+        if (ship) {
+            CUX(launch_push_row_list((int)vb, y_local, dst0, n_dst, by_mc ? 1 : 0, x.boundary_rows, x.n_boundary_rows, S));
+            ++h->launches_per_spmv;
+        }
+    }
+    if (ship && by_ce) {
         for (int k = 0; k < world; k++) {
             if (k == rank) continue;
             CUX(cudaEventRecord(x.ev_ce_done[k], x.ce[k]));
             CUX(cudaStreamWaitEvent(S, x.ev_ce_done[k], 0));
         }
+    } else if (ship) {
+        CUX(cudaEventRecord(x.ev_ship_done, x.ship));
+        CUX(cudaStreamWaitEvent(S, x.ev_ship_done, 0));
+    }
     if (barriers) {
         CUX(launch_flag_barrier(ex->flags, rank, world, 1, x.epoch, x.status, ex->timeout_ms, S));
         ++h->launches_per_spmv;

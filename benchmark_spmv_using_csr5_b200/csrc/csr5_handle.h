@@ -9,20 +9,25 @@
 
 namespace csr5 {
 
-constexpr int MAX_CHUNKS = 64;
-
 // Streams / events / cached row-block boundaries of csr5b200_spmv_allgather (created at its first call).
 struct ExchangeState {
     bool ready = false;
     bool warmed = false;       // every kernel of the step has been launched once (module loading is done)
     cudaStream_t work1 = nullptr;                       // odd row blocks (even ones run on the handle's stream)
-    cudaStream_t side = nullptr;                        // carry passes, SM pushes, entry barrier
+    cudaStream_t side = nullptr;                        // carry passes, entry barrier
+    cudaStream_t ship = nullptr;                        // SM transports: the push kernels
     cudaStream_t ce[CSR5B200_MAX_SCATTER] = {};         // copy-engine transport: one stream per destination
     cudaEvent_t ev_begin = nullptr, ev_side_done = nullptr, ev_work1_done = nullptr;
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {}, ev_cal[MAX_CHUNKS] = {};
     cudaEvent_t ev_ce_done[CSR5B200_MAX_SCATTER] = {};
     int chunks = 0;                                     // row blocks the cached boundaries are for
     std::vector<int> chunk_tile, chunk_row;             // chunks + 1 boundaries: tiles, rows
+    std::vector<int> chunk_carried;                     // row chunk_row[c] began before block c (boundary row)
+    std::vector<int> chunk_order;                       // execution order of the blocks
+    ChunkTable table;                                   // the same for the boundary pass
+    int boundary_rows[MAX_CHUNKS] = {};
+    int n_boundary_rows = 0;
+    cudaEvent_t ev_ship_done = nullptr;
     uint32_t *epoch = nullptr;                          // device: 2 words, barrier epochs of the entry / exit slot
     int *status = nullptr;                              // device: != 0 after a barrier timed out
     int last_transport = 0, last_chunks = 0;

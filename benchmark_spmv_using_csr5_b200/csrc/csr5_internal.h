@@ -93,6 +93,15 @@ struct ShardCtx {
     int exchange = 0;               // 0 auto, 1 fused (SpMV kernels store to every destination), 2 push (copy pass after)
 };
 
+// Row blocks of the overlapped exchange: block c = tiles [tile_begin[c], tile_begin[c + 1]); skip_row[c] = the row
+// that crosses INTO block c from an earlier block (its carries are held back for the boundary pass), or -1.
+constexpr int MAX_CHUNKS = 64;
+struct ChunkTable {
+    int n = 0;
+    int tile_begin[MAX_CHUNKS + 1] = {};
+    int skip_row[MAX_CHUNKS] = {};
+};
+
 // Which parts of an SpMV one launch group enqueues.  A whole spmv() = everything on over all tiles; the
 // overlapped multi-GPU exchange (csr5_exchange.cu) cuts the tiles into row blocks.
 struct SpmvCall {
@@ -102,6 +111,8 @@ struct SpmvCall {
     bool prologue = true;   // clear (beta = 0) / scale (beta != 0) the rows no tile stores; refresh the hot-column table
     bool tiles = true;      // the main kernel over the tiles (+ tail)
     bool calibrate = true;  // the carry pass over the same tiles (+ the tail tile's carry)
+    int skip_row = -1;      // carry pass: leave out the carries into this row (a row that began in an earlier row block)
+    const ChunkTable *boundary = nullptr;   // != nullptr: ONLY the boundary pass -- the held-back carries of all blocks
 };
 
 // Enqueues the selected parts of y = alpha * A * x + beta * y; in the legacy sharded mode (sh != nullptr) the rows
@@ -115,6 +126,11 @@ cudaError_t launch_spmv_part_f32(const Plan &pl, const SpmvTuning &tn, float alp
 // addresses, or one NVSwitch multicast address) with `grid` CTAs.
 cudaError_t launch_push_rows(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
                              long long rows, int grid, cudaStream_t stream);
+
+// y_local[rows[i]] -> the same element of every destination, i < n <= MAX_CHUNKS (the rows that cross row-block
+// boundaries, final only after the boundary pass).
+cudaError_t launch_push_row_list(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
+                                 const int *rows, int n, cudaStream_t stream);
 
 // ---- cross-GPU barrier on flag words in peer-mapped memory (csr5_exchange.cu) ------------------------------
 // flags[k] = base of rank k's flag array as mapped here (>= 2 * world words each, zero-initialised).  Rank r

@@ -594,12 +594,55 @@ spmv_hot_kernel(const SpmvArgs<VT> a, const VT *__restrict__ hot_x, const uint32
 
 // ---- carries: y[row of tile t] += calibrator[t] for the tiles whose first row began earlier -----
 template <typename VT>
-__global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a, const int t_begin, const int t_end)
+__global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a, const int t_begin, const int t_end,
+                                                        const int skip_row)
 {
     const int t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t_end) return;
     const VT c = a.cal[t];
-    if (c != (VT)0) atomicAdd(a.y + (a.tile_ptr[t] & ROW_MASK), c);   // local HBM only, also when sharded
+    const int row = (int)(a.tile_ptr[t] & ROW_MASK);
+    if (c != (VT)0 && row != skip_row) atomicAdd(a.y + row, c);   // local HBM only, also when sharded
+}
+
+// Boundary pass of the row-block cut (csr5_exchange.cu): the carries a block's carry pass left out because their row
+// began in an EARLIER block -- applied once every block's tiles are done, in whatever order the blocks ran.
+template <typename VT>
+__global__ void __launch_bounds__(256) calibrate_boundary_kernel(const SpmvArgs<VT> a, const ChunkTable tb)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.p) return;
+    int lo = 0, hi = tb.n;                        // block of tile t: last c with tile_begin[c] <= t (the tail tile p - 1
+    while (hi - lo > 1) {                         // belongs to the last block)
+        const int mid = (lo + hi) >> 1;
+        if (tb.tile_begin[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int skip = tb.skip_row[lo];
+    if (skip < 0) return;
+    const VT c = a.cal[t];
+    if (c != (VT)0 && (int)(a.tile_ptr[t] & ROW_MASK) == skip) atomicAdd(a.y + skip, c);
+}
+
+template <typename VT>
+struct RowListArgs {
+    const VT *y_local;
+    VT *dst[CSR5B200_MAX_SCATTER];
+    int n_dst, multicast, n;
+    int rows[MAX_CHUNKS];
+};
+
+template <typename VT> __global__ void push_row_list_kernel(const RowListArgs<VT> a)
+{
+    const int i = threadIdx.x;
+    if (i >= a.n) return;
+    const int r = a.rows[i];
+    const VT v = a.y_local[r];
+    if (a.multicast) {
+        multimem_store<VT>(a.dst[0] + r, v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < CSR5B200_MAX_SCATTER; k++)
+            if (k < a.n_dst) a.dst[k][r] = v;
+    }
 }
 
 // ---- sharded mode, "push" exchange: copy this rank's finished y segment to every destination ----------
@@ -851,6 +894,13 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
     const bool tail = call.tail && pl.p > 0;
     a.tail_warps = tail ? (pl.m - pl.tail_start + 31) / 32 : 0;
     const int threads = 256;
+    if (call.boundary) {
+        if (pl.p > 0) {
+            calibrate_boundary_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a, *call.boundary);
+            ++*launches;
+        }
+        return cudaGetLastError();
+    }
 
     if (call.prologue) {
         // rows that no tile and no tail warp stores: the empty rows in front of the tail
@@ -897,7 +947,7 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
     if (call.calibrate && pl.p > 0) {
         const int cb = a.tile_begin, ce = tail ? pl.p : a.tile_end;   // the tail tile's carry is calibrator[p - 1]
         if (ce > cb) {
-            calibrate_kernel<VT><<<(ce - cb + threads - 1) / threads, threads, 0, stream>>>(a, cb, ce);   // local HBM only
+            calibrate_kernel<VT><<<(ce - cb + threads - 1) / threads, threads, 0, stream>>>(a, cb, ce, call.skip_row);   // local HBM only
             ++*launches;
         }
         if (fused) {
@@ -915,6 +965,22 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
         push_rows_kernel<VT><<<tn.num_sms * 4, PUSH_THREADS, 0, stream>>>(pa);
         ++*launches;
     }
+    return cudaGetLastError();
+}
+
+template <typename VT>
+cudaError_t launch_push_row_list_t(const VT *y_local, VT *const *dst, int n_dst, int multicast, const int *rows, int n,
+                                   cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    RowListArgs<VT> ra;
+    ra.y_local = y_local;
+    for (int k = 0; k < CSR5B200_MAX_SCATTER; k++) ra.dst[k] = k < n_dst ? dst[k] : nullptr;
+    ra.n_dst = n_dst;
+    ra.multicast = multicast;
+    ra.n = n > MAX_CHUNKS ? MAX_CHUNKS : n;
+    for (int i = 0; i < ra.n; i++) ra.rows[i] = rows[i];
+    push_row_list_kernel<VT><<<1, MAX_CHUNKS, 0, stream>>>(ra);
     return cudaGetLastError();
 }
 

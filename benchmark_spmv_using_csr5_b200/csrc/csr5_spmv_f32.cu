@@ -13,4 +13,10 @@ cudaError_t launch_push_rows_f32(const void *y_local, void *const *dst, int n_ds
     return launch_push_t<float>(static_cast<const float *>(y_local), reinterpret_cast<float *const *>(dst), n_dst, multicast,
                              rows, grid, stream);
 }
+cudaError_t launch_push_row_list_f32(const void *y_local, void *const *dst, int n_dst, int multicast, const int *rows,
+                                     int n, cudaStream_t stream)
+{
+    return launch_push_row_list_t<float>(static_cast<const float *>(y_local), reinterpret_cast<float *const *>(dst), n_dst,
+                                      multicast, rows, n, stream);
+}
 }  // namespace csr5

@@ -13,4 +13,10 @@ cudaError_t launch_push_rows_f64(const void *y_local, void *const *dst, int n_ds
     return launch_push_t<double>(static_cast<const double *>(y_local), reinterpret_cast<double *const *>(dst), n_dst, multicast,
                              rows, grid, stream);
 }
+cudaError_t launch_push_row_list_f64(const void *y_local, void *const *dst, int n_dst, int multicast, const int *rows,
+                                     int n, cudaStream_t stream)
+{
+    return launch_push_row_list_t<double>(static_cast<const double *>(y_local), reinterpret_cast<double *const *>(dst), n_dst,
+                                      multicast, rows, n, stream);
+}
 }  // namespace csr5

@@ -41,7 +41,8 @@ for stage in "$@"; do
     mtests)
       PORT=$((PORT+1))
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${rest:-2} --master-addr 127.0.0.1 --master-port $PORT \
-        tests/multigpu_worker.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -12 | tee gpurun_out/${TAG}_mtests_n${rest:-2}.txt ;;
+        tests/multigpu_worker.py > gpurun_out/${TAG}_mtests_n${rest:-2}.txt 2>&1
+      echo "rc=$?"; grep -E "rank [0-9]+:|Error|error|assert|Traceback|File " gpurun_out/${TAG}_mtests_n${rest:-2}.txt | head -30 ;;
     probe)
       timeout 1500 python tools/gpu/probe.py ${rest:-c3,c5,c2} 2>&1 | tee gpurun_out/${TAG}_probe.txt | tail -60 ;;
     sigma)

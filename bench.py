@@ -765,11 +765,38 @@ def e2e_sharded(torch, dist, sh, w, rank, world, device, n, m, m_total, vb, dtyp
     windows.append((h0, time.perf_counter()))
     e_ms = rank_max(ev0.elapsed_time(ev1) / steps)
     sh.setX(w["x"])
+
+    # the host link alone: the same uploads and downloads with nothing in between, both directions at once on all
+    # ranks -- what this box's PCIe / host memory can carry, i.e. the floor of any end-to-end step
+    def copies():
+        b = state["k"] % nbuf
+        with torch.cuda.stream(s_in):
+            x_dev[b][xs0:xs1].copy_(x_host[b], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            y_host[b].copy_(sh.y_local, non_blocking=True)
+        state["k"] += 1
+    for _ in range(2):
+        copies()
+    sync_streams()
+    ev0.record(main)
+    for s_ in (s_in, s_out):
+        s_.wait_stream(main)
+    for _ in range(steps):
+        copies()
+    main.wait_stream(s_in)
+    main.wait_stream(s_out)
+    ev1.record(main)
+    sync_streams()
+    copy_ms = rank_max(ev0.elapsed_time(ev1) / steps)
     rt = 1e-12 if vb == 8 else 1e-5
     for yh in y_host:
         assert torch.allclose(yh.to(device), sh.y_local, rtol=rt, atol=0), "host-buffer path disagrees with the device path"
     return {"value": 2.0 * total_nnz / (e_ms * 1e6), "unit": "GFLOP/s", "h2d_bytes_per_step": n * vb,
             "d2h_bytes_per_step": m_total * vb, "ms_per_step": e_ms, "steps": steps,
+            "host_link_floor_ms_per_step": copy_ms,
+            "host_link_GBps_both_directions_all_ranks": (n * vb + m_total * vb) / (copy_ms * 1e6),
+            "host_link_note": "the same pinned uploads and downloads with no work in between, H2D and D2H concurrently on "
+                              "all ranks: the floor this box's host link sets for any end-to-end step",
             "api": ("per rank and step: pinned H2D of its 1/N slice of x, NCCL all-gather of x, ShardedCsr5.spmv (SpMV + "
                     "overlapped y exchange), D2H of the rank's y rows; four streams, two buffers each, software-pipelined; "
                     "bytes are whole-job totals")}

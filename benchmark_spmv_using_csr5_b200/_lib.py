@@ -72,6 +72,8 @@ SIGNATURES = {
     "csr5b200_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "csr5b200_get_info": (C.c_int, [C.c_void_p, C.POINTER(Csr5Info)]),
     "csr5b200_get_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
+    "csr5b200_coo_to_csr": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "csr5b200_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "csr5b200_copy_meta_to_host": (C.c_int, [C.c_void_p] * 6),
     "csr5b200_spmv_host": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),

@@ -44,11 +44,14 @@ def main(argv=None) -> int:
     print(f"PRECISION = {'64-bit Double Precision' if vb == 8 else '32-bit Single Precision'}")
     print("------------------------------------------------------")
     print(f"--------------{args.filename}--------------")
+    torch.cuda.set_device(0)
     try:
-        m, n, row_ptr, col, _file_val = mmio.read_mtx(args.filename, np_dt)
+        # text parsing on the host, COO -> CSR (symmetric expansion + stable sort by row, main.cu:239-306) on the device
+        m, n, d_rp, d_ci, _file_val = mmio.read_mtx_device(args.filename, np_dt)
     except mmio.MatrixMarketError as e:
         print(e)
         return 2
+    row_ptr, col = d_rp.cpu().numpy(), d_ci.cpu().numpy()   # for the sequential CPU yardstick below
     nnz = len(col)
     val, x = mmio.reference_values(nnz, n, np_dt, args.seed)   # the file's values are discarded (main.cu:314-326)
     print(f" ( {m}, {n} ) nnz = {nnz}")
@@ -62,10 +65,9 @@ def main(argv=None) -> int:
     print(f"cpu sequential time = {ref_ms:.6g} ms. Bandwidth = {gb / (1e6 * ref_ms):.6g} GB/s. "
           f"GFlops = {gflop / (1e6 * ref_ms):.6g} GFlops.\n")
 
-    torch.cuda.set_device(0)
     prop = torch.cuda.get_device_properties(0)
     print(f"Device [0] {prop.name},  @ {getattr(prop, 'clock_rate', 0) * 1e-3:g}MHz. ")
-    d_rp, d_ci = torch.from_numpy(row_ptr).cuda(), torch.from_numpy(col).cuda()
+    d_ci = d_ci.contiguous()
     d_val, d_x = torch.from_numpy(val).cuda(), torch.from_numpy(x).cuda()
     d_y = torch.zeros(m, device="cuda", dtype=t_dt)
 

@@ -265,6 +265,10 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
         case CSR5B200_OPT_HOT_COLUMNS: h->tune.hot_columns = value; break;
         case CSR5B200_OPT_HOT_THREADS: h->tune.hot_threads = value; break;
+        case CSR5B200_OPT_CACHE_POLICY:
+            if (value < 0 || value > 3) return CSR5B200_INVALID_ARGUMENT;
+            h->tune.cache_policy = value;
+            break;
         case CSR5B200_OPT_SIGMA_RULE:
             if (value < 0 || value > 1) return CSR5B200_INVALID_ARGUMENT;
             h->sigma_rule = value;
@@ -710,6 +714,7 @@ const char *csr5b200_error_string(int code)
         case CSR5B200_UNSUPPORTED_VALUE_TYPE: return "unsupported value type (use 4 or 8 bytes)";
         case CSR5B200_CUDA_ERROR: return "CUDA runtime error (see csr5b200_info.last_cuda_error)";
         case CSR5B200_INVALID_ARGUMENT: return "invalid argument";
+        case CSR5B200_EXCHANGE_TIMEOUT: return "a device-side barrier of the sharded step timed out waiting for a peer";
         default: return "unrecognised error code";
     }
 }

@@ -187,6 +187,8 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
                                          table r/s/t/u = 4/32/256/6 (anonymouslib_cuda.h:297-313; keeps the CSR5 arrays word for
                                          word those of the reference), 1 the rule measured on B200 (profiles/r02_sigma_rule.md); the environment variable
                                          CSR5B200_SIGMA_RULE=b200 sets it for every handle of an unmodified caller */
+#define CSR5B200_OPT_CACHE_POLICY  13 /* tuning, direct-load kernel: bit 0 = the val/col stream does not allocate in L1, bit 1 = the x
+                                         gathers carry an L2 evict_last hint (for x larger than L2); 0 = default */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays
@@ -226,6 +228,19 @@ CSR5B200_API int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out);
  * main SpMV kernel of the spmv() calls since the last call of this function, oldest first, at most
  * `capacity` (and at most 4096 are retained).  Synchronises the stream.  *count = number written. */
 CSR5B200_API int csr5b200_get_kernel_times(csr5b200_handle_t h, float *ms, int capacity, int *count);
+
+/* COO -> CSR on the device with the semantics of the reference's loader (CSR5_cuda/main.cu:211-306, the same
+ * loops in every backend's main): 0-based (row, col[, val]) triples in file order; with symmetric != 0 every
+ * off-diagonal (i, j) also yields (j, i) right after it (main.cu:239-246, 271-289; the reference does this for
+ * symmetric and hermitian files, not for skew-symmetric ones); rows are filled in emission order -- a STABLE sort by
+ * row: columns are not sorted inside a row, duplicates are kept.  vals == NULL: pattern file, every value is 1.
+ * All pointers are device pointers except nnz_out (host).  row_ptr has m + 1 entries; col_out / val_out have
+ * `capacity` entries.  *nnz_out = entries of the CSR (nnz + mirrored ones); call with col_out == NULL to only
+ * count (row_ptr is scratch then).  CSR5B200_INVALID_ARGUMENT: an index is out of range, or capacity is too small.
+ * Synchronous on `cuda_stream`. */
+CSR5B200_API int csr5b200_coo_to_csr(int m, int n, int nnz, const int *rows, const int *cols, const void *vals,
+                                     int value_bytes, int symmetric, int *row_ptr, int *col_out, void *val_out,
+                                     int capacity, int *nnz_out, void *cuda_stream);
 
 /* Microbenchmarks on the matrix held by the handle (CSR5 format, no hot-column table): the SpMV's launch shape and
  * col stream with the kernel stripped down to one component, to MEASURE the floors quoted in DESIGN.md

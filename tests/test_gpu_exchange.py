@@ -9,8 +9,6 @@
   y -> x feedback) with device 0 standing in for every peer.
 """
 import os
-import subprocess
-import sys
 
 import numpy as np
 import pytest
@@ -183,34 +181,73 @@ def test_native_sharded_iterate_feeds_y_back_as_x(torch_cuda, oracle):
         sh.destroy()
 
 
-def test_flag_barriers_two_shards_one_gpu():
-    """The device-side flag barrier (what the multi-process mode uses between GPUs) with two shards on device 0.
-    Run in a child process with enough hardware queues that the two shards' streams never alias (a spinning
-    barrier kernel must not sit in front of the kernel it waits for); the barrier's own time-out turns any
-    such stall into an error instead of a hang."""
-    code = r'''
-import sys, numpy as np
-sys.path.insert(0, %r)
-import oracle
-from benchmark_spmv_using_csr5_b200 import matrices as M, sharded as S
-A = M.example_c1()
-val, x = M.values(A.nnz, A.n, "int", np.float64)
-y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
-for transport in ("push", "ce"):
-    sh = S.ShardedCsr5Native([0, 0], np.float64)
-    sh.inputCSR(A.m, A.n, A.row_ptr, A.col, val)
-    sh.set_exchange(transport, chunks=2, push_ctas=2, barrier=S.BARRIER_FLAGS, timeout_ms=4000)
-    sh.setX(x); sh.asCSR5()
-    for _ in range(4):
-        sh.spmv(1.0)
-    sh.synchronize()
-    assert np.array_equal(sh.y(0), y_ref) and np.array_equal(sh.y(1), y_ref), transport
-    sh.destroy()
-print("FLAGS OK")
-''' % ROOT
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
-    assert r.returncode == 0 and "FLAGS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+def _rank0_of_two(torch, A, val, x, sigma, transport, flags0, flags1, y0, y1, timeout_ms=3000, chunks=3):
+    """One spmv_allgather call as rank 0 of a world of 2 whose 'peer' lives in buffers on the same GPU."""
+    from benchmark_spmv_using_csr5_b200 import _lib, handle as H
+    from benchmark_spmv_using_csr5_b200 import sharded as S
+    bounds = S.row_partition(A.row_ptr, 2)
+    rp, ci, v = S.shard_csr(A.row_ptr, A.col, val, bounds[0], bounds[1])
+    tdt = torch.float64 if val.dtype == np.float64 else torch.float32
+    keep = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (rp, ci, v, x)]
+    h = H.anonymouslibHandle(int(bounds[1]), A.n, tdt)
+    assert h.inputCSR(int(ci.size), keep[0], keep[1], keep[2]) == 0 and h.setX(keep[3]) == 0
+    h.setSigma(sigma)
+    assert h.asCSR5() == 0
+    ex = _lib.Csr5Exchange()
+    ex.rank, ex.world = 0, 2
+    ex.y_full[0], ex.y_full[1] = y0.data_ptr(), y1.data_ptr()
+    ex.flags[0], ex.flags[1] = flags0.data_ptr(), flags1.data_ptr()
+    ex.row_begin, ex.chunks, ex.push_ctas, ex.timeout_ms = 0, chunks, 2, timeout_ms
+    ex.transport = H.TRANSPORT_NAMES[transport]
+    return h, ex, keep, int(bounds[1])
+
+
+@pytest.mark.parametrize("transport", ["ce", "push", "inkernel"])
+def test_flag_barrier_and_peer_delivery_as_rank0_of_two(torch_cuda, oracle, transport):
+    """The multi-process step on one GPU, deterministically: this process is rank 0 of 2, the peer's y buffer and flag
+    words are plain device buffers, and the peer's barrier arrivals are written in advance (epochs far ahead), so the
+    device-side barrier never has to spin for a kernel that shares the GPU with it.  Checks: rank 0's rows land in
+    the peer's buffer, both barrier slots signal the peer with increasing epochs, nothing times out."""
+    torch = torch_cuda
+    A = M.example_c1()
+    val, x = M.values(A.nnz, A.n, "int", np.float64)
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    flags0 = torch.zeros(64, device="cuda", dtype=torch.int32)
+    flags1 = torch.zeros(64, device="cuda", dtype=torch.int32)
+    flags0[1] = 1000      # slot 0 (entry), word [0 * world + peer]: the peer is far ahead
+    flags0[2 + 1] = 1000  # slot 1 (exit)
+    y0 = torch.full((A.m,), float("nan"), device="cuda", dtype=torch.float64)
+    y1 = torch.full((A.m,), float("nan"), device="cuda", dtype=torch.float64)
+    h, ex, _keep, rows0 = _rank0_of_two(torch, A, val, x, -1, transport, flags0, flags1, y0, y1)
+    for step in range(1, 4):
+        ex.entry_barrier = 1
+        assert h.spmv_allgather(1.0, 0.0, ex) == 0
+        assert h.exchange_status() == 0
+        assert np.array_equal(y0[:rows0].cpu().numpy(), y_ref[:rows0])
+        assert np.array_equal(y1[:rows0].cpu().numpy(), y_ref[:rows0]), "rank 0's rows did not reach the peer's buffer"
+        assert torch.isnan(y1[rows0:]).all() and torch.isnan(y0[rows0:]).all()   # the peer's rows are the peer's job
+        f1 = flags1.cpu().numpy()
+        assert f1[0 * 2 + 0] == step and f1[1 * 2 + 0] == step, f1[:4]           # entry / exit arrival of rank 0
+        y1[:rows0] = float("nan")
+    h.free()
+
+
+def test_flag_barrier_times_out_instead_of_hanging(torch_cuda):
+    """A peer that never arrives: the barrier gives up after timeout_ms and the status call reports it."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    A = M.banded(2000, 16)
+    val, x = M.values(A.nnz, A.n, "int", np.float64)
+    flags0 = torch.zeros(64, device="cuda", dtype=torch.int32)
+    flags1 = torch.zeros(64, device="cuda", dtype=torch.int32)
+    y0 = torch.zeros(A.m, device="cuda", dtype=torch.float64)
+    y1 = torch.zeros(A.m, device="cuda", dtype=torch.float64)
+    h, ex, _keep, _rows0 = _rank0_of_two(torch, A, val, x, 16, "push", flags0, flags1, y0, y1, timeout_ms=200)
+    assert h.spmv_allgather(1.0, 0.0, ex) == 0
+    assert h.exchange_status() == H.EXCHANGE_TIMEOUT
+    assert "timed out" in h.error_string(H.EXCHANGE_TIMEOUT)
+    assert h.exchange_status() == 0   # reported once
+    h.free()
 
 
 def test_native_sharded_argument_errors(torch_cuda):

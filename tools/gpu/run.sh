@@ -56,7 +56,14 @@ for stage in "$@"; do
       wl=${rest%%:*}; r2=${rest#*:}; rx=${r2%%:*}; extra=${r2#*:}; [ "$extra" == "$r2" ] && extra=""
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$rx -s 10 -c 2 -f -o gpurun_out/${TAG}_ncu_${wl}_${rx} \
         python bench.py --workload $wl --steps 12 --warmup 3 --no-cpu-baseline --no-e2e --no-extra ${extra//,/ } > gpurun_out/${TAG}_ncu_${wl}_${rx}.log 2>&1
-      echo "rc=$?"; ls -la gpurun_out/${TAG}_ncu_${wl}_${rx}.ncu-rep ;;
+      echo "rc=$?"; rep=gpurun_out/${TAG}_ncu_${wl}_${rx}
+      # gpurun brings back at most 64 MiB: keep the small exports, drop the 40 MB report unless KEEP_REP=1
+      python tools/ncu_summary.py $rep.ncu-rep > $rep.md 2>/dev/null
+      ncu -i $rep.ncu-rep --page raw --csv 2>/dev/null | gzip > ${rep}_raw.csv.gz
+      ncu -i $rep.ncu-rep --page details 2>/dev/null > ${rep}_details.txt
+      ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | gzip > ${rep}_source.csv.gz
+      [ "${KEEP_REP:-0}" == "1" ] || rm -f $rep.ncu-rep
+      ls -la ${rep}*; head -12 $rep.md ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

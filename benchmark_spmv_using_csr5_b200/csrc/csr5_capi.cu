@@ -95,22 +95,26 @@ int auto_sigma(int m, int nnz)
 
 // CSR5B200_OPT_SIGMA_RULE = 1: the table measured on B200 (profiles/r02_sigma_rule.md; sweep of nnz/row 2..300 x
 // {FP64, FP32} x sigma 4..32, tools/gpu/sweep_sigma.py), replacing the reference's Maxwell-era one above.  Same input
-// (k = nnz / m) so that it stays a drop-in for setSigma(AUTO).  What the sweep shows: tiles of a few hundred bytes
-// (sigma = k for short rows) cost 10-30 %; FP64 tiles whose val slab is a power of two in bytes (sigma 8, 16, 32:
-// 2 / 4 / 8 KB strides between concurrently streaming warps) lose 4-6 % to their neighbours; beyond that the curve
-// is flat within 1-3 %.
+// (k = nnz / m) so that it stays a drop-in for setSigma(AUTO).  What the sweep shows and the rule keeps:
+//   * short rows: sigma = k makes tiles of a few hundred bytes whose descriptor / tile_ptr / launch overhead costs
+//     8-16 % (FP64) and 16-29 % (FP32) against sigma 12-16 -> a floor on sigma;
+//   * k > 256: the reference falls back to sigma = 6 (its `u`), 7 % (FP64) to 33 % (FP32) slower than 32;
+//   * 12 <= k <= 256: every sigma from 12 up is within 1-4 % and the ranking changes from box to box and with the
+//     matrix size (profiles/r02_ab_parked_row_stores.txt: sigma 16 beats 14 by 4 % on C2 where the sweep's 4 M-row
+//     matrix had it 2 % behind) -> the reference's choice is kept there.
 int auto_sigma_b200(int m, int nnz, int value_bytes)
 {
     const int k = m > 0 ? nnz / m : 0;
     if (value_bytes == 8) {
         if (k <= 2) return 4;
         if (k <= 5) return 12;
-        return 14;
+        if (k <= 11) return 14;
+    } else {
+        if (k <= 2) return 8;
+        if (k == 3) return 12;
+        if (k <= 11) return 16;
     }
-    if (k <= 2) return 8;
-    if (k == 3) return 12;
-    if (k <= 22) return 16;
-    return 24;
+    return k <= 32 ? k : 32;
 }
 
 // Hot-column table: pick the most referenced columns of the CSR5 tiles, at most
@@ -265,10 +269,6 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
         case CSR5B200_OPT_HOT_COLUMNS: h->tune.hot_columns = value; break;
         case CSR5B200_OPT_HOT_THREADS: h->tune.hot_threads = value; break;
-        case CSR5B200_OPT_CACHE_POLICY:
-            if (value < 0 || value > 3) return CSR5B200_INVALID_ARGUMENT;
-            h->tune.cache_policy = value;
-            break;
         case CSR5B200_OPT_SIGMA_RULE:
             if (value < 0 || value > 1) return CSR5B200_INVALID_ARGUMENT;
             h->sigma_rule = value;

@@ -59,7 +59,6 @@ struct SpmvTuning {
     int hot_columns = 0;   // 0 off (default), -1 auto (kept if it serves >= 25 % of the references), > 0 capacity
     int hot_threads = 0;   // tuning: threads per CTA of the hot-column kernel (0 = default)
     int exchange = 0;      // sharded mode: 0 auto, 1 fused, 2 push
-    int cache_policy = 0;  // CSR5B200_OPT_CACHE_POLICY bits
     cudaEvent_t ev_begin = nullptr;  // optional: recorded right before / after the main SpMV kernel
     cudaEvent_t ev_end = nullptr;
 };

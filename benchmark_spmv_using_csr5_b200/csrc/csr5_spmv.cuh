@@ -78,7 +78,6 @@ struct SpmvArgs {
     // Sharded (multi-GPU) mode (csr5b200_spmv_scatter): `y` is this rank's segment in local HBM; the
     // n_dst destination segments -- this rank's slot in each GPU's concatenated y, mapped over NVLink,
     // or ONE NVSwitch multicast address that replicates a store to all of them -- receive copies.
-    int cache_policy;    // CSR5B200_OPT_CACHE_POLICY bits (direct kernel)
     int n_dst;
     int dst_multicast;   // 1: y_dst[0] is a multicast (multimem) address
     VT *y_dst[CSR5B200_MAX_SCATTER];
@@ -139,40 +138,6 @@ __device__ __forceinline__ uint32_t unpack_flags(uint32_t w0, uint32_t w1, int b
     return f;
 }
 
-// Cache-policy experiments of the direct kernel (CSR5B200_OPT_CACHE_POLICY bits):
-//   bit 0: the val / col stream does not allocate in L1 (ld.global.nc.L1::no_allocate) -- leaves L1 to the x lines;
-//   bit 1: the x gathers carry an L2 evict_last hint -- for x vectors larger than L2 (R-MAT 25: 268 MB).
-__device__ __forceinline__ double ld_stream_noalloc(const double *p)
-{
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_stream_noalloc(const float *p)
-{
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ int ld_stream_noalloc(const int *p)
-{
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ double ld_x_hint(const double *p, uint64_t pol)
-{
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ld_x_hint(const float *p, uint64_t pol)
-{
-    float v;
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-
 // Where a tile's val / col / descriptor words come from.
 template <typename VT>
 struct GlobalTile {  // direct-load kernel: streaming loads, evict-first
@@ -181,21 +146,13 @@ struct GlobalTile {  // direct-load kernel: streaming loads, evict-first
     const VT *val;
     const int *col;
     const uint32_t *desc;
-    int policy;
-    uint64_t x_policy;
-    __device__ __forceinline__ VT v(int i, int lane) const
-    {
-        return (policy & 1) ? ld_stream_noalloc(val + i * OMEGA + lane) : __ldcs(val + i * OMEGA + lane);
-    }
-    __device__ __forceinline__ int c(int i, int lane) const
-    {
-        return (policy & 1) ? ld_stream_noalloc(col + i * OMEGA + lane) : __ldcs(col + i * OMEGA + lane);
-    }
+    // Measured and dropped (profiles/r02_probe_cache_policy.txt): val / col through ld.global.nc.L1::no_allocate and
+    // x gathers with an L2 evict_last hint move R-MAT 22 / 25 by less than 1 % -- L1TEX and L2 are both at ~80 % of
+    // their peak throughput either way -- while the extra operands cost 14 registers per thread.
+    __device__ __forceinline__ VT v(int i, int lane) const { return __ldcs(val + i * OMEGA + lane); }
+    __device__ __forceinline__ int c(int i, int lane) const { return __ldcs(col + i * OMEGA + lane); }
     __device__ __forceinline__ uint32_t d(int k, int lane) const { return __ldg(desc + k * OMEGA + lane); }
-    __device__ __forceinline__ VT xv(const VT *__restrict__ x, int c) const
-    {
-        return (policy & 2) ? ld_x_hint(x + c, x_policy) : __ldg(x + c);
-    }
+    __device__ __forceinline__ VT xv(const VT *__restrict__ x, int c) const { return __ldg(x + c); }
 };
 
 // Direct loads as GlobalTile, but a column index with bit 31 set names a slot of the hot-column
@@ -313,6 +270,9 @@ __device__ __forceinline__ void process_tile(const SpmvArgs<VT> &a, const Tile &
     // directly when it closes.  Lane 0's first segment (row_start itself) is handled at the end.
     bool open = (ff & 1u) && lane != 0;
     VT sum = 0, first_sum = 0;
+    // (Measured and dropped, profiles/r02_ab_parked_row_stores.txt: parking the first two finished rows of a lane in
+    // registers and storing them warp-wide after the loop -- fewer store instructions, i.e. fewer L1TEX wavefronts --
+    // costs 8 registers and one resident CTA per SM: C2 -2..-7 %, C3 / C5 -1 %, C4 +-2 %.)
 #pragma unroll
     for (int c0 = 0; c0 < SIGMA; c0 += CH) {
         VT v[CH], xv[CH];
@@ -412,8 +372,7 @@ __global__ void __launch_bounds__(WPB * 32) spmv_direct_kernel(const SpmvArgs<VT
     if (tl >= a.tile_end) return;
     const int t = (int)tl;
     const size_t base = (size_t)t * (OMEGA * SIGMA);
-    GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet, a.cache_policy,
-                        (a.cache_policy & 2) ? l2_evict_last_policy() : 0ull};
+    GlobalTile<VT> tile{a.val + base, a.col + base, a.desc + (size_t)t * OMEGA * a.num_packet};
     process_tile<VT, SIGMA, MULTI, GlobalTile<VT>, NCH>(a, tile, t, lane, __ldg(a.tile_ptr + t),
                                                         __ldg(a.tile_ptr + t + 1));
 }
@@ -928,7 +887,6 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
     a.cal = static_cast<VT *>(pl.calibrator);
     a.alpha = alpha;
     a.beta = beta;
-    a.cache_policy = tn.cache_policy;
     a.m = pl.m;
     a.p = pl.p;
     a.bit_y = pl.bit_y;

@@ -49,7 +49,6 @@ OPT_HOT_COLUMNS = 9
 OPT_HOT_THREADS = 10
 OPT_EXCHANGE = 11
 OPT_SIGMA_RULE = 12
-OPT_CACHE_POLICY = 13
 SIGMA_RULE_REFERENCE, SIGMA_RULE_B200 = 0, 1
 EXCHANGE_AUTO, EXCHANGE_FUSED, EXCHANGE_PUSH = 0, 1, 2
 # csr5b200_spmv_allgather transports (CSR5B200_TRANSPORT_*)

@@ -187,8 +187,6 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
                                          table r/s/t/u = 4/32/256/6 (anonymouslib_cuda.h:297-313; keeps the CSR5 arrays word for
                                          word those of the reference), 1 the rule measured on B200 (profiles/r02_sigma_rule.md); the environment variable
                                          CSR5B200_SIGMA_RULE=b200 sets it for every handle of an unmodified caller */
-#define CSR5B200_OPT_CACHE_POLICY  13 /* tuning, direct-load kernel: bit 0 = the val/col stream does not allocate in L1, bit 1 = the x
-                                         gathers carry an L2 evict_last hint (for x larger than L2); 0 = default */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays

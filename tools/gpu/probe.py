@@ -100,7 +100,8 @@ for name in (sys.argv[1] if len(sys.argv) > 1 else "c3,c5,c2").split(","):
     # ---- variants ----------------------------------------------------------------------------------------------
     res["variants"] = {}
     if name in ("c3", "c5"):
-        for label, kw in (("nch1", dict(nch=1)), ("nch3", dict(nch=3)), ("wpb8", dict(wpb=8)), ("wpb2", dict(wpb=2)),
+        for label, kw in (("sigma14", dict(sigma=14)), ("sigma10", dict(sigma=10)),
+                          ("nch1", dict(nch=1)), ("nch3", dict(nch=3)), ("wpb8", dict(wpb=8)), ("wpb2", dict(wpb=2)),
                           ("hot_auto", dict(hot=-1)), ("hot_4096_t1024", dict(hot=4096, hot_threads=1024)),
                           ("hot_8192_t1024", dict(hot=8192, hot_threads=1024)),
                           ("hot_16384_t768", dict(hot=16384, hot_threads=768)),

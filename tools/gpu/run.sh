@@ -64,6 +64,18 @@ for stage in "$@"; do
       ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | gzip > ${rep}_source.csv.gz
       [ "${KEEP_REP:-0}" == "1" ] || rm -f $rep.ncu-rep
       ls -la ${rep}*; head -12 $rep.md ;;
+    ab)
+      # A/B of two builds of the library on the same box, interleaved: ab:<other .so>:<bench args>
+      other=${rest%%:*}; a=${rest#*:}; [ "$a" == "$rest" ] && a=""
+      for rep in 1 2; do for lib in libcsr5_b200.so $other; do
+        CSR5B200_LIB=$lib timeout 900 python bench.py --no-cpu-baseline --no-e2e --steps 100 ${a//,/ } 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+ex=d.get('extra_workloads') or {}
+print('$lib rep $rep:', d['config']['workload'][:24], 'sigma', d['config']['sigma'], 'kernel_ms %.4f frac %.3f' % (d['roofline']['kernel_ms_avg'], d['roofline']['frac']),
+      ' | '.join('%s sigma %s kernel_ms %.4f frac %.3f' % (k, v.get('sigma'), v.get('kernel_ms', 0), v.get('roofline_frac', 0)) for k, v in ex.items()))
+" | tee -a gpurun_out/${TAG}_ab.txt
+      done; done ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

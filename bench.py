@@ -636,6 +636,7 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
     ms_step = rank_max(timed_loop(torch, step, max(args.warmup, 3), steps, windows, sync_all))
     assert all_ok(sh.exchange_status() == 0), "a device-side barrier timed out"
     info = A.info()
+    default_transport, default_chunks = info.exchange_transport, info.exchange_chunks
     launches = info.launches_per_spmv
     t = torch.tensor([nnz], device=device, dtype=torch.int64)
     dist.all_reduce(t)
@@ -649,6 +650,17 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
         S.allgather_v(sh.y_full, bounds, rank)
     ms_nccl = rank_max(timed_loop(torch, nccl_step, 3, k2, None, sync_all))
 
+    trace = None
+    if args.trace_exchange and exch == "overlap":
+        A.set_option(H.OPT_EXCHANGE_TRACE, 1)
+        for _ in range(3):
+            step()
+        blocks, end = A.exchange_trace()
+        A.set_option(H.OPT_EXCHANGE_TRACE, 0)
+        mine = {"rank": rank, "rows": m, "blocks_ms_tiles_carry_shipped": blocks, "end_ms": end}
+        allt = [None] * world
+        dist.all_gather_object(allt, mine)
+        trace = allt
     variants = {}
     if args.sweep_exchange and exch == "overlap":
         for spec in args.sweep_exchange.split("+"):
@@ -666,10 +678,11 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
         sh.transport, sh.chunks, sh.push_ctas = H.TRANSPORT_NAMES[args.transport], args.chunks, args.push_ctas
 
     if exch == "overlap":
-        xi = A.info()
-        mode = (f"overlap: SpMV in row blocks, finished blocks shipped by "
-                f"{ {1: 'the copy engines', 2: 'a push grid (unicast peer stores)', 3: 'a push grid (NVSwitch multicast)', 4: 'the SpMV kernel itself', 5: 'nobody'}.get(sh.transport or 1) }"
-                f"; device-side flag barrier; y double-buffered")
+        xi = A.info()   # transport / row blocks the (auto) rule resolved to in the last default step
+        how = {1: "the copy engines", 2: "a push grid (unicast peer stores)", 3: "a push grid (NVSwitch multicast stores)",
+               4: "the SpMV kernel itself (peer stores as tiles complete)", 5: "nobody"}.get(default_transport, "?")
+        mode = (f"overlap: SpMV in {default_chunks} row block(s), finished blocks shipped by {how}; device-side flag "
+                f"barrier; y double-buffered")
     elif exch == "nccl":
         mode = "nccl all-gather after the SpMV"
     else:
@@ -683,7 +696,7 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
              "nvlink_time_floor_ms": in_bytes / (link_gbs * 1e6),
              "step_floor_ms": max(ms_local, in_bytes / (link_gbs * 1e6)),
              "frac_of_step_floor": max(ms_local, in_bytes / (link_gbs * 1e6)) / ms_step,
-             "exchange_variants_ms": variants or None,
+             "exchange_variants_ms": variants or None, "exchange_trace": trace,
              "note": "every rank ends each step holding all of y: (N-1)/N of y must enter each GPU over NVLink per "
                      "step, which bounds the step from below next to the HBM stream"}
     out = dict(name=name, m=m, n=n, nnz=nnz, total_nnz=total_nnz, m_total=m_total, vb=vb, dtype=dtype, ms_step=ms_step,
@@ -834,7 +847,8 @@ def main_multi(args, torch, H, device, rank, world, local_rank):
                   "ms_N_spmv_only_no_exchange": c5r["ms_local"], "exchange": c5r["multi"]["exchange"],
                   "ms_N_spmv_then_nccl_allgather": c5r["multi"]["ms_per_step_spmv_then_nccl_allgather"],
                   "parity_max_rel_err": c5r["max_rel"], "parity": "pass (every rank's gathered y, element-wise)",
-                  "exchange_variants_ms": c5r["multi"]["exchange_variants_ms"]}
+                  "exchange_variants_ms": c5r["multi"]["exchange_variants_ms"],
+                  "exchange_trace": c5r["multi"]["exchange_trace"]}
         except Exception as e:
             c5 = {"error": f"{type(e).__name__}: {e}"}
             log(f"[bench] rank {rank}: c5 strong-scaling measurement failed: {c5['error']}")
@@ -907,6 +921,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="overlap: row blocks per step (0 = default)")
     ap.add_argument("--push-ctas", type=int, default=0, help="overlap, SM transports: CTAs of the push grid (0 = default)")
     ap.add_argument("--sweep-exchange", default="", help="overlap: also time these variants, e.g. 'ce/8+push/8/32+multicast/8/32' (transport/chunks/push CTAs)")
+    ap.add_argument("--trace-exchange", action="store_true", help="overlap: per-row-block timeline of one step on every rank")
     ap.add_argument("--scheme", type=int, default=0, help="fused modes: 0 auto, 1 in-kernel stores, 2 push pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -64,6 +64,7 @@ SIGNATURES = {
     "csr5b200_spmv_axpby": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     "csr5b200_spmv_allgather": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.POINTER(Csr5Exchange)]),
     "csr5b200_exchange_status": (C.c_int, [C.c_void_p]),
+    "csr5b200_exchange_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int)]),
     "csr5b200_spmv_scatter": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
                                          C.c_int]),
     "csr5b200_destroy": (C.c_int, [C.c_void_p]),

@@ -147,7 +147,8 @@ int build_hot_table(csr5b200_handle_t h)
     CUH(cudaMalloc(&out2, 2 * sizeof(unsigned long long)));
     CUH(cudaMemsetAsync(cnt, 0, (size_t)pl.n * sizeof(int), h->stream));
     CUH(launch_hot_count(pl.col, limit, cnt, h->tune.num_sms, h->stream));
-    // smallest threshold whose column set fits the table (set size is non-increasing in the threshold)
+    // smallest threshold whose column set fits the table (set size is non-increasing in the threshold): from the
+    // histogram of the counts in ONE pass and one read-back; counts beyond the last bin fall back to bisection
     unsigned long long res[2] = {0, 0};
     auto count_ge = [&](long long thr) -> cudaError_t {
         cudaError_t e = launch_hot_count_ge(cnt, pl.n, (int)thr, out2, h->tune.num_sms, h->stream);
@@ -157,12 +158,42 @@ int build_hot_table(csr5b200_handle_t h)
         return cudaStreamSynchronize(h->stream);
     };
     long long lo = 1, hi = limit + 1;   // invariant: set(hi) fits; set(lo - 1) does not (or lo == 1)
+    {
+        const int bins = hot_hist_bins();
+        unsigned int *d_cols = nullptr;
+        unsigned long long *d_refs = nullptr;
+        std::vector<unsigned int> hc(bins);
+        std::vector<unsigned long long> hr(bins);
+        cudaError_t e = cudaMalloc(&d_cols, bins * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMalloc(&d_refs, bins * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = launch_hot_hist(cnt, pl.n, d_cols, d_refs, h->tune.num_sms, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hc.data(), d_cols, bins * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hr.data(), d_refs, bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(d_cols);
+        cudaFree(d_refs);
+        if (e != cudaSuccess) return done(cuda_fail(h, e));
+        unsigned long long cols = 0, refs = 0;
+        int t = bins - 1;
+        if (hc[t] > (unsigned int)capacity) {
+            lo = bins - 1;                       // even the clamped top bin overflows the table: bisect above it
+        } else {
+            for (; t >= 1; t--) {
+                if (cols + hc[t] > (unsigned long long)capacity) break;
+                cols += hc[t];
+                refs += hr[t];
+            }
+            lo = hi = t + 1;                     // threshold t + 1: everything counted so far
+            res[0] = cols;
+            res[1] = refs;
+        }
+    }
     while (lo < hi) {
         const long long mid = lo + (hi - lo) / 2;
         CUH(count_ge(mid));
         if (res[0] <= (unsigned long long)capacity) hi = mid; else lo = mid + 1;
     }
-    CUH(count_ge(lo));
+    if (res[0] == 0 || lo >= hot_hist_bins() - 1) CUH(count_ge(lo));
     const int threshold = (int)lo;
     const int hot_k = (int)res[0];
     const double coverage = limit > 0 ? (double)res[1] / (double)limit : 0.0;
@@ -269,6 +300,8 @@ int csr5b200_set_option(csr5b200_handle_t h, int option, int value)
         case CSR5B200_OPT_DIRECT_NCH: h->tune.direct_nch = value; break;
         case CSR5B200_OPT_HOT_COLUMNS: h->tune.hot_columns = value; break;
         case CSR5B200_OPT_HOT_THREADS: h->tune.hot_threads = value; break;
+        case CSR5B200_OPT_EXCHANGE_TRACE: h->ex.trace = value != 0; break;
+        case CSR5B200_OPT_DETERMINISTIC: h->tune.deterministic = value != 0; break;
         case CSR5B200_OPT_SIGMA_RULE:
             if (value < 0 || value > 1) return CSR5B200_INVALID_ARGUMENT;
             h->sigma_rule = value;

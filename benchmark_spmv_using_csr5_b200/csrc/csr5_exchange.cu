@@ -118,6 +118,11 @@ void release_exchange(csr5b200_handle_t h)
     for (auto &e : x.ev_chunk) de(e);
     for (auto &e : x.ev_cal) de(e);
     for (auto &e : x.ev_ce_done) de(e);
+    de(x.tv_begin);
+    de(x.tv_end);
+    for (auto &e : x.tv_tiles) de(e);
+    for (auto &e : x.tv_cal) de(e);
+    for (auto &e : x.tv_ship) de(e);
     cudaFree(x.epoch);
     cudaFree(x.status);
     x = ExchangeState();
@@ -345,6 +350,20 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
     }
     const bool ship = transport != CSR5B200_TRANSPORT_NONE;
     const bool by_ce = transport == CSR5B200_TRANSPORT_COPY_ENGINE;
+    const bool trace = x.trace;
+    if (trace) {
+        if (!x.tv_begin) {
+            CUX(cudaEventCreate(&x.tv_begin));
+            CUX(cudaEventCreate(&x.tv_end));
+            for (int i = 0; i < MAX_CHUNKS; i++) {
+                CUX(cudaEventCreate(&x.tv_tiles[i]));
+                CUX(cudaEventCreate(&x.tv_cal[i]));
+                CUX(cudaEventCreate(&x.tv_ship[i]));
+            }
+        }
+        x.traced_chunks = chunks;
+        CUX(cudaEventRecord(x.tv_begin, S));
+    }
     const bool by_mc = transport == CSR5B200_TRANSPORT_SM_MULTICAST;
     CUX(cudaEventRecord(x.ev_begin, S));
     CUX(cudaStreamWaitEvent(x.side, x.ev_begin, 0));
@@ -376,6 +395,7 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         blk.calibrate = false;
         CUX(spmv_part(h, alpha, beta, y_local, nullptr, blk, W));
         CUX(cudaEventRecord(x.ev_chunk[i], W));
+        if (trace) CUX(cudaEventRecord(x.tv_tiles[i], W));
 
         // carry pass of the block (all but the carries into the row that crossed in), then its rows leave
         CUX(cudaStreamWaitEvent(x.side, x.ev_chunk[i], 0));
@@ -384,6 +404,10 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         cal.calibrate = true;
         cal.skip_row = x.table.skip_row[c];
         CUX(spmv_part(h, alpha, beta, y_local, nullptr, cal, x.side));
+        if (trace) {
+            CUX(cudaEventRecord(x.tv_cal[i], x.side));
+            x.traced_ship[i] = false;
+        }
         const long long ra = (long long)x.chunk_row[c] + (x.chunk_carried[c] ? 1 : 0), rb = x.chunk_row[c + 1];
         if (!ship || rb <= ra) continue;
         CUX(cudaEventRecord(x.ev_cal[i], x.side));
@@ -402,6 +426,10 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
             CUX(cudaStreamWaitEvent(x.ship, x.ev_cal[i], 0));
             CUX(launch_push_rows((int)vb, src, dst, n_dst, by_mc ? 1 : 0, rb - ra, push_ctas, x.ship));
             ++h->launches_per_spmv;
+            if (trace) {
+                CUX(cudaEventRecord(x.tv_ship[i], x.ship));
+                x.traced_ship[i] = true;
+            }
         }
     }
 
@@ -435,8 +463,30 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         CUX(launch_flag_barrier(ex->flags, rank, world, 1, x.epoch, x.status, ex->timeout_ms, S));
         ++h->launches_per_spmv;
     }
+    if (trace) CUX(cudaEventRecord(x.tv_end, S));
     x.last_transport = transport;
     x.last_chunks = chunks;
+    return CSR5B200_SUCCESS;
+}
+
+int csr5b200_exchange_trace(csr5b200_handle_t h, float *ms, int capacity, int *count)
+{
+    if (!h || !count || (capacity > 0 && !ms)) return CSR5B200_INVALID_ARGUMENT;
+    *count = 0;
+    ExchangeState &x = h->ex;
+    if (!x.trace || !x.tv_begin || x.traced_chunks <= 0) return CSR5B200_SUCCESS;
+    CUX(cudaStreamSynchronize(h->stream));
+    auto put = [&](cudaEvent_t e, bool valid) {
+        float v = -1.f;
+        if (valid && cudaEventElapsedTime(&v, x.tv_begin, e) != cudaSuccess) { v = -1.f; cudaGetLastError(); }
+        if (*count < capacity) ms[(*count)++] = v;
+    };
+    for (int i = 0; i < x.traced_chunks; i++) {
+        put(x.tv_tiles[i], true);
+        put(x.tv_cal[i], true);
+        put(x.tv_ship[i], x.traced_ship[i]);
+    }
+    put(x.tv_end, true);
     return CSR5B200_SUCCESS;
 }
 

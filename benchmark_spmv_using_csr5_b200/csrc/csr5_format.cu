@@ -377,6 +377,40 @@ hot_count_ge_kernel(const int *__restrict__ cnt, int n, int threshold, unsigned 
     if ((threadIdx.x & 31) == 0 && cols) { atomicAdd(out2, cols); atomicAdd(out2 + 1, refs); }
 }
 
+// One pass over the column reference counts: cols[v] = number of columns with min(cnt, HOT_BINS - 1) == v and
+// refs[v] = the references they receive.  The host picks the threshold from the two histograms (one read-back
+// instead of a bisection of ~30 synchronising launches).  Low counts -- almost every column of a power-law matrix
+// -- are accumulated in shared memory first.
+constexpr int HOT_BINS = 65536;
+constexpr int HOT_SMEM_BINS = 2048;
+
+__global__ void __launch_bounds__(256)
+hot_hist_kernel(const int *__restrict__ cnt, int n, unsigned int *__restrict__ cols, unsigned long long *__restrict__ refs)
+{
+    __shared__ unsigned int s_cols[HOT_SMEM_BINS];
+    for (int t = threadIdx.x; t < HOT_SMEM_BINS; t += blockDim.x) s_cols[t] = 0;
+    __syncthreads();
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+        const int v = cnt[c];
+        if (v <= 0) continue;
+        if (v < HOT_SMEM_BINS) {
+            atomicAdd(&s_cols[v], 1u);
+        } else {
+            const int b = v < HOT_BINS ? v : HOT_BINS - 1;
+            atomicAdd(cols + b, 1u);
+            atomicAdd(refs + b, (unsigned long long)v);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < HOT_SMEM_BINS; t += blockDim.x) {
+        const unsigned int k = s_cols[t];
+        if (k) {
+            atomicAdd(cols + t, k);
+            atomicAdd(refs + t, (unsigned long long)k * (unsigned long long)t);   // every column of bin t has count t
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) hot_flags_kernel(const int *__restrict__ cnt, int n, int threshold, int *slot)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,6 +504,18 @@ cudaError_t launch_hot_count_ge(const int *cnt, int n, int threshold, unsigned l
     cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     hot_count_ge_kernel<<<num_sms * 4, 256, 0, stream>>>(cnt, n, threshold, out2);
+    return cudaGetLastError();
+}
+
+int hot_hist_bins() { return HOT_BINS; }
+
+cudaError_t launch_hot_hist(const int *cnt, int n, unsigned int *cols, unsigned long long *refs, int num_sms,
+                            cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(cols, 0, HOT_BINS * sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(refs, 0, HOT_BINS * sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+    hot_hist_kernel<<<num_sms * 4, 256, 0, stream>>>(cnt, n, cols, refs);
     return cudaGetLastError();
 }
 

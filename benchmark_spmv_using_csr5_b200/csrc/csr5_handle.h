@@ -31,6 +31,12 @@ struct ExchangeState {
     uint32_t *epoch = nullptr;                          // device: 2 words, barrier epochs of the entry / exit slot
     int *status = nullptr;                              // device: != 0 after a barrier timed out
     int last_transport = 0, last_chunks = 0;
+    // CSR5B200_OPT_EXCHANGE_TRACE: timing events of the last step (csr5b200_exchange_trace)
+    bool trace = false;
+    cudaEvent_t tv_begin = nullptr, tv_end = nullptr;
+    cudaEvent_t tv_tiles[MAX_CHUNKS] = {}, tv_cal[MAX_CHUNKS] = {}, tv_ship[MAX_CHUNKS] = {};
+    int traced_chunks = 0;
+    bool traced_ship[MAX_CHUNKS] = {};
 };
 
 }  // namespace csr5

@@ -59,6 +59,7 @@ struct SpmvTuning {
     int hot_columns = 0;   // 0 off (default), -1 auto (kept if it serves >= 25 % of the references), > 0 capacity
     int hot_threads = 0;   // tuning: threads per CTA of the hot-column kernel (0 = default)
     int exchange = 0;      // sharded mode: 0 auto, 1 fused, 2 push
+    int deterministic = 0; // carries of a row are summed in tile order by one thread (no atomics): run-to-run identical bits
     cudaEvent_t ev_begin = nullptr;  // optional: recorded right before / after the main SpMV kernel
     cudaEvent_t ev_end = nullptr;
 };
@@ -75,6 +76,9 @@ cudaError_t launch_exclusive_scan(int *data, int n, void *scratch, size_t scratc
 cudaError_t launch_hot_count(const int *col, long long limit, int *cnt, int num_sms, cudaStream_t stream);
 cudaError_t launch_hot_count_ge(const int *cnt, int n, int threshold, unsigned long long *out2, int num_sms,
                                 cudaStream_t stream);
+int hot_hist_bins();
+cudaError_t launch_hot_hist(const int *cnt, int n, unsigned int *cols, unsigned long long *refs, int num_sms,
+                            cudaStream_t stream);
 cudaError_t launch_hot_flags(const int *cnt, int n, int threshold, int *slot, cudaStream_t stream);
 cudaError_t launch_hot_assign(const int *cnt, int n, int threshold, const int *slot, int *hot_col, int *col,
                               long long limit, int num_sms, cudaStream_t stream);

@@ -611,6 +611,23 @@ __global__ void __launch_bounds__(256) calibrate_kernel(const SpmvArgs<VT> a, co
     if (c != (VT)0 && row != skip_row) atomicAdd(a.y + row, c);   // local HBM only, also when sharded
 }
 
+// Deterministic carry pass (CSR5B200_OPT_DETERMINISTIC): the first tile of every run of tiles that carry into the same
+// row sums the run's carries in tile order and adds them to y with one plain read-modify-write -- no atomics, so the
+// bits do not depend on the order in which warps retire.  Runs are long only for hub rows (R-MAT 22: <= 203 tiles).
+template <typename VT>
+__global__ void __launch_bounds__(256) calibrate_ordered_kernel(const SpmvArgs<VT> a, const int t_begin, const int t_end,
+                                                                const int skip_row)
+{
+    const int t = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_end) return;
+    const uint32_t row = a.tile_ptr[t] & ROW_MASK;
+    if ((int)row == skip_row) return;
+    if (t > t_begin && (a.tile_ptr[t - 1] & ROW_MASK) == row) return;   // not the first tile of its run
+    VT sum = 0;
+    for (int u = t; u < t_end && (a.tile_ptr[u] & ROW_MASK) == row; u++) sum += a.cal[u];
+    if (sum != (VT)0) a.y[row] += sum;
+}
+
 // Boundary pass of the row-block cut (csr5_exchange.cu): the carries a block's carry pass left out because their row
 // began in an EARLIER block -- applied once every block's tiles are done, in whatever order the blocks ran.
 template <typename VT>
@@ -954,7 +971,10 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
     if (call.calibrate && pl.p > 0) {
         const int cb = a.tile_begin, ce = tail ? pl.p : a.tile_end;   // the tail tile's carry is calibrator[p - 1]
         if (ce > cb) {
-            calibrate_kernel<VT><<<(ce - cb + threads - 1) / threads, threads, 0, stream>>>(a, cb, ce, call.skip_row);   // local HBM only
+            if (tn.deterministic)
+                calibrate_ordered_kernel<VT><<<(ce - cb + threads - 1) / threads, threads, 0, stream>>>(a, cb, ce, call.skip_row);
+            else
+                calibrate_kernel<VT><<<(ce - cb + threads - 1) / threads, threads, 0, stream>>>(a, cb, ce, call.skip_row);   // local HBM only
             ++*launches;
         }
         if (fused) {

@@ -49,6 +49,8 @@ OPT_HOT_COLUMNS = 9
 OPT_HOT_THREADS = 10
 OPT_EXCHANGE = 11
 OPT_SIGMA_RULE = 12
+OPT_DETERMINISTIC = 13
+OPT_EXCHANGE_TRACE = 14
 SIGMA_RULE_REFERENCE, SIGMA_RULE_B200 = 0, 1
 EXCHANGE_AUTO, EXCHANGE_FUSED, EXCHANGE_PUSH = 0, 1, 2
 # csr5b200_spmv_allgather transports (CSR5B200_TRANSPORT_*)
@@ -139,6 +141,17 @@ class anonymouslibHandle:
 
     def exchange_status(self) -> int:
         return self._lib.csr5b200_exchange_status(self._h)
+
+    def exchange_trace(self):
+        """Timeline of the last traced step (OPT_EXCHANGE_TRACE): list of [tiles_done, carry_done, shipped] ms per row
+        block in execution order, and the end of the step."""
+        buf = (C.c_float * 256)()
+        cnt = C.c_int(0)
+        err = self._lib.csr5b200_exchange_trace(self._h, buf, 256, C.byref(cnt))
+        if err:
+            raise RuntimeError(self.error_string(err))
+        v = [round(float(t), 4) for t in buf[:cnt.value]]
+        return [v[i:i + 3] for i in range(0, len(v) - 1, 3)], (v[-1] if v else None)
 
     def spmv_scatter(self, alpha: float, y_local, y_dst, n_dst: int, multicast: bool = False) -> int:
         """Sharded mode (csr5b200_spmv_scatter): ``y_local`` is this shard's y segment (CUDA tensor in local

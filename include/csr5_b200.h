@@ -155,6 +155,10 @@ typedef struct csr5b200_exchange {
 /* y_full[rank][row_begin + i] = alpha * (A_shard x)_i + beta * (old value), i < m, delivered to every rank as
  * described above.  Same return codes as spmv(). */
 CSR5B200_API int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, const csr5b200_exchange *ex);
+/* With CSR5B200_OPT_EXCHANGE_TRACE on: the timeline of the last step on this shard, in ms since the step began, three
+ * values per row block in execution order -- SpMV tiles done, carry pass done, rows shipped (-1: nothing shipped by an
+ * SM transport) -- and finally the end of the step (after the exit barrier).  Synchronises the stream. */
+CSR5B200_API int csr5b200_exchange_trace(csr5b200_handle_t h, float *ms, int capacity, int *count);
 /* Synchronises the handle's stream; returns CSR5B200_EXCHANGE_TIMEOUT if a barrier gave up since the last call. */
 #define CSR5B200_EXCHANGE_TIMEOUT (-102)
 CSR5B200_API int csr5b200_exchange_status(csr5b200_handle_t h);
@@ -187,6 +191,10 @@ CSR5B200_API int csr5b200_set_stream(csr5b200_handle_t h, void *cuda_stream);
                                          table r/s/t/u = 4/32/256/6 (anonymouslib_cuda.h:297-313; keeps the CSR5 arrays word for
                                          word those of the reference), 1 the rule measured on B200 (profiles/r02_sigma_rule.md); the environment variable
                                          CSR5B200_SIGMA_RULE=b200 sets it for every handle of an unmodified caller */
+#define CSR5B200_OPT_DETERMINISTIC 13 /* 1 = spmv() / spmv_axpby() add the carries of a row in tile order, one thread per row, instead
+                                         of with floating-point atomics (replaces csr5_spmv_cuda.h:313-382, which mixes both): the
+                                         result is bit-identical from run to run also for rows that span several tiles; 0 = default */
+#define CSR5B200_OPT_EXCHANGE_TRACE 14 /* 1 = csr5b200_spmv_allgather records timing events per row block (csr5b200_exchange_trace) */
 CSR5B200_API int csr5b200_set_option(csr5b200_handle_t h, int option, int value);
 
 /* Introspection for tests and harnesses: scalars + device pointers of the CSR5 arrays

@@ -520,3 +520,28 @@ def test_sigma_rule_b200_is_bit_exact_too(torch_cuda, oracle):
                 got, want = h.meta_to_host(), oracle.csr5_meta(A.m, A.nnz, s, A.row_ptr)
                 assert np.array_equal(got["tile_ptr"], want.tile_ptr) and np.array_equal(got["desc"], want.desc)
                 h.free()
+
+
+def test_deterministic_carry_pass(torch_cuda, oracle):
+    """CSR5B200_OPT_DETERMINISTIC: rows that span many tiles (their carries are otherwise added with floating-point
+    atomics, in the order the warps retire) come out bit-identical from run to run, and still within tolerance."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    for name in ("hub_row_s12", "empty_rows_long_row_s4", "rmat12_auto", "m1_one_row", "example_c1_auto"):
+        _n, A, sigma = [c for c in CASES if c[0] == name][0]
+        for dt, tdt, tol in ((np.float64, torch.float64, FP64_RTOL), (np.float32, torch.float32, FP32_RTOL)):
+            val, x = M.values(A.nnz, A.n, "real", dt)
+            h, _keep = _handle(torch, A, val, x, sigma, kernel=1)
+            assert h.set_option(H.OPT_DETERMINISTIC, 1) == 0
+            ys = [_spmv(torch, h, A.m, tdt) for _ in range(6)]
+            for y in ys[1:]:
+                assert np.array_equal(y, ys[0]), f"{name}: run-to-run bits differ in deterministic mode"
+            ref = oracle.csr_spmv_f32_acc64(A.m, A.row_ptr, A.col, val, x) if dt == np.float32 else \
+                oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+            assert np.allclose(ys[0], ref, rtol=tol, atol=1e-5 if dt == np.float32 else 0), name
+            vali, xi = M.values(A.nnz, A.n, "int", dt)
+            h2, _k2 = _handle(torch, A, vali, xi, sigma, kernel=1)
+            h2.set_option(H.OPT_DETERMINISTIC, 1)
+            assert np.array_equal(_spmv(torch, h2, A.m, tdt), oracle.csr_spmv(A.m, A.row_ptr, A.col, vali, xi)), name
+            h.free()
+            h2.free()

@@ -46,6 +46,7 @@ WORKLOADS = {
     "c4": "27-pt Laplacian 320^3, FP32 (BASELINE.json configs[3])",
     "c5": "R-MAT scale 25, edge factor 16, FP64, row-range sharded by balanced nnz (BASELINE.json configs[4])",
 }
+ROW_WEIGHT = [8.0]   # --row-weight: strong-scaling workloads balance nnz + w * rows per shard instead of nnz alone
 STRONG = {"c3", "c5"}   # fixed matrix split over the ranks (strong scaling); c2 grows with N (weak)
 
 
@@ -186,7 +187,7 @@ def build_workload(name, torch, device, rank, world):
         n = rp.numel() - 1
         dtype = torch.float64
         val, x = M.device_values(ci.numel(), n, "real", dtype, device, seed=42)
-        bounds = S.row_partition(rp, world)
+        bounds = S.row_partition(rp, world, row_weight=ROW_WEIGHT[0])
         if world > 1:
             lrp, lci, lval = S.shard_csr(rp, ci, val, int(bounds[rank]), int(bounds[rank + 1]))
             lrp, lci, lval = lrp.contiguous(), lci.clone(), lval.clone()
@@ -559,7 +560,8 @@ def make_sharded(S, w, n, args, exch, transport=None, chunks=None, push_ctas=Non
     return S.ShardedCsr5(w["bounds"], n, w["row_ptr"], w["col"], w["val"], mode="overlap",
                          transport=transport if transport is not None else args.transport,
                          chunks=chunks if chunks is not None else args.chunks,
-                         push_ctas=push_ctas if push_ctas is not None else args.push_ctas, **kw)
+                         push_ctas=push_ctas if push_ctas is not None else args.push_ctas,
+                         push_threads=args.push_threads, **kw)
 
 
 def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows, steps, full):
@@ -665,17 +667,20 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
     if args.sweep_exchange and exch == "overlap":
         for spec in args.sweep_exchange.split("+"):
             tr, _, rest = spec.partition("/")
-            ch, _, ctas = rest.partition("/")
+            ch, _, rest2 = rest.partition("/")
+            ctas, _, thr = rest2.partition("/")
             if tr == "multicast" and not sh.has_multicast:
                 variants[spec] = "no multicast address"
                 continue
             sh.transport = H.TRANSPORT_NAMES[tr]
             sh.chunks = int(ch or 0)
             sh.push_ctas = int(ctas or 0)
+            sh.push_threads = int(thr or 0)
             v = rank_max(timed_loop(torch, step, 3, k2, None, sync_all))
             st_ok = all_ok(sh.exchange_status() == 0)
             variants[spec] = v if st_ok else "barrier timeout"
         sh.transport, sh.chunks, sh.push_ctas = H.TRANSPORT_NAMES[args.transport], args.chunks, args.push_ctas
+        sh.push_threads = args.push_threads
 
     if exch == "overlap":
         xi = A.info()   # transport / row blocks the (auto) rule resolved to in the last default step
@@ -701,7 +706,8 @@ def measure_sharded(torch, dist, H, S, name, args, device, rank, world, windows,
                      "step, which bounds the step from below next to the HBM stream"}
     out = dict(name=name, m=m, n=n, nnz=nnz, total_nnz=total_nnz, m_total=m_total, vb=vb, dtype=dtype, ms_step=ms_step,
                gflops=2.0 * total_nnz / (ms_step * 1e6), info=info, max_rel=max_rel, convert_ms=float(np.median(conv[1:])),
-               convert_ms_all=conv, launches=launches, multi=multi, ms_local=ms_local, e2e=None, exch=exch)
+               convert_ms_all=conv, launches=launches, multi=multi, ms_local=ms_local, e2e=None, exch=exch,
+               bounds=[int(b) for b in bounds])
 
     # ---- end to end, pipelined: every step uploads x and downloads y ---------------------------------------------
     if full and not args.no_e2e:
@@ -845,6 +851,9 @@ def main_multi(args, torch, H, device, rank, world, local_rank):
             c5 = {"workload": WORKLOADS["c5"], "ms_1gpu": ms1, "roofline_frac_1gpu": frac1, "ms_N": c5r["ms_step"],
                   "speedup": ms1 / c5r["ms_step"], "gflops_N": c5r["gflops"], "nnz": c5r["total_nnz"],
                   "ms_N_spmv_only_no_exchange": c5r["ms_local"], "exchange": c5r["multi"]["exchange"],
+                  "partition": f"contiguous row ranges balancing nnz + {args.row_weight:g} * rows per shard "
+                               "(a shard's SpMV costs its non-zeros, its share of the y exchange its rows)",
+                  "rows_per_shard": [int(b - a) for a, b in zip(c5r["bounds"][:-1], c5r["bounds"][1:])],
                   "ms_N_spmv_then_nccl_allgather": c5r["multi"]["ms_per_step_spmv_then_nccl_allgather"],
                   "parity_max_rel_err": c5r["max_rel"], "parity": "pass (every rank's gathered y, element-wise)",
                   "exchange_variants_ms": c5r["multi"]["exchange_variants_ms"],
@@ -885,6 +894,8 @@ def main_multi(args, torch, H, device, rank, world, local_rank):
             "csr_to_csr5_ms": r["convert_ms"], "csr_to_csr5_ms_samples": r["convert_ms_all"],
             "parity_max_rel_err_vs_fp64_segment_sums": r["max_rel"],
             "parity": "every rank's gathered y compared element-wise with the all-gathered per-rank FP64 references",
+            "rows_per_shard": [int(b - a) for a, b in zip(r["bounds"][:-1], r["bounds"][1:])],
+            "partition_row_weight": args.row_weight if args.workload in STRONG else None,
         },
         "clocks": sampler.summary(windows),
         "e2e": r["e2e"],
@@ -921,6 +932,11 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="overlap: row blocks per step (0 = default)")
     ap.add_argument("--push-ctas", type=int, default=0, help="overlap, SM transports: CTAs of the push grid (0 = default)")
     ap.add_argument("--sweep-exchange", default="", help="overlap: also time these variants, e.g. 'ce/8+push/8/32+multicast/8/32' (transport/chunks/push CTAs)")
+    ap.add_argument("--push-threads", type=int, default=0, help="overlap, SM transports: threads per CTA of the push grid")
+    ap.add_argument("--row-weight", type=float, default=8.0,
+                    help="strong-scaling workloads (c3 / c5 on N > 1 GPUs): shards balance nnz + w * rows; 0 = nnz alone.  Measured "
+                         "on 8 B200 with R-MAT 25 (profiles/r02_bench_c5_n8_rowweight*.json): w = 0 / 2 / 4 / 6 / 8 -> 0.70-0.74 / 0.68 / "
+                         "0.62 / 0.60 / 0.58 ms per step")
     ap.add_argument("--trace-exchange", action="store_true", help="overlap: per-row-block timeline of one step on every rank")
     ap.add_argument("--scheme", type=int, default=0, help="fused modes: 0 auto, 1 in-kernel stores, 2 push pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -930,6 +946,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true")
     args = ap.parse_args()
     capture_stdout()
+    ROW_WEIGHT[0] = args.row_weight
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)

@@ -48,7 +48,7 @@ class Csr5Exchange(C.Structure):
         ("y_full", C.c_void_p * MAX_SCATTER), ("y_multicast", C.c_void_p),
         ("flags", C.c_void_p * MAX_SCATTER), ("row_begin", C.c_longlong),
         ("chunks", C.c_int), ("transport", C.c_int), ("entry_barrier", C.c_int),
-        ("push_ctas", C.c_int), ("timeout_ms", C.c_int),
+        ("push_ctas", C.c_int), ("timeout_ms", C.c_int), ("push_threads", C.c_int),
     ]
 
 
@@ -88,6 +88,7 @@ SIGNATURES = {
     "csr5b200_sharded_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "csr5b200_sharded_input_csr_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                                    C.c_void_p]),
+    "csr5b200_sharded_set_partition": (C.c_int, [C.c_void_p, C.c_double]),
     "csr5b200_sharded_set_sigma": (C.c_int, [C.c_void_p, C.c_int]),
     "csr5b200_sharded_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "csr5b200_sharded_set_exchange": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -82,8 +82,8 @@ cudaError_t launch_flag_barrier(uint32_t *const *flags, int rank, int world, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_push_rows_f64(const void *, void *const *, int, int, long long, int, cudaStream_t);
-cudaError_t launch_push_rows_f32(const void *, void *const *, int, int, long long, int, cudaStream_t);
+cudaError_t launch_push_rows_f64(const void *, void *const *, int, int, long long, int, int, cudaStream_t);
+cudaError_t launch_push_rows_f32(const void *, void *const *, int, int, long long, int, int, cudaStream_t);
 
 cudaError_t launch_push_row_list_f64(const void *, void *const *, int, int, const int *, int, cudaStream_t);
 cudaError_t launch_push_row_list_f32(const void *, void *const *, int, int, const int *, int, cudaStream_t);
@@ -96,10 +96,10 @@ cudaError_t launch_push_row_list(int value_bytes, const void *y_local, void *con
 }
 
 cudaError_t launch_push_rows(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
-                             long long rows, int grid, cudaStream_t stream)
+                             long long rows, int grid, int threads, cudaStream_t stream)
 {
-    return value_bytes == 8 ? launch_push_rows_f64(y_local, dst, n_dst, multicast, rows, grid, stream)
-                            : launch_push_rows_f32(y_local, dst, n_dst, multicast, rows, grid, stream);
+    return value_bytes == 8 ? launch_push_rows_f64(y_local, dst, n_dst, multicast, rows, grid, threads, stream)
+                            : launch_push_rows_f32(y_local, dst, n_dst, multicast, rows, grid, threads, stream);
 }
 
 void release_exchange(csr5b200_handle_t h)
@@ -309,7 +309,7 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         SpmvCall all;
         cudaError_t e = spmv_part(h, alpha, beta, scratch, nullptr, all, S);
         void *none[CSR5B200_MAX_SCATTER] = {};
-        if (e == cudaSuccess) e = launch_push_rows((int)vb, scratch, none, 0, 0, pl.m < 1024 ? pl.m : 1024, 1, S);
+        if (e == cudaSuccess) e = launch_push_rows((int)vb, scratch, none, 0, 0, pl.m < 1024 ? pl.m : 1024, 1, 256, S);
         if (e == cudaSuccess) e = launch_flag_barrier(nullptr, 0, 0, 0, x.epoch, x.status, 0, S);
         if (e == cudaSuccess) e = cudaStreamSynchronize(S);
         cudaFree(scratch);
@@ -424,7 +424,7 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
             void *dst[CSR5B200_MAX_SCATTER] = {};
             for (int k = 0; k < n_dst; k++) dst[k] = static_cast<char *>(dst0[k]) + (size_t)ra * vb;
             CUX(cudaStreamWaitEvent(x.ship, x.ev_cal[i], 0));
-            CUX(launch_push_rows((int)vb, src, dst, n_dst, by_mc ? 1 : 0, rb - ra, push_ctas, x.ship));
+            CUX(launch_push_rows((int)vb, src, dst, n_dst, by_mc ? 1 : 0, rb - ra, push_ctas, ex->push_threads, x.ship));
             ++h->launches_per_spmv;
             if (trace) {
                 CUX(cudaEventRecord(x.tv_ship[i], x.ship));

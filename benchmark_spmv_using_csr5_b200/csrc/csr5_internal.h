@@ -129,7 +129,7 @@ cudaError_t launch_spmv_part_f32(const Plan &pl, const SpmvTuning &tn, float alp
 // SM transport of the overlapped exchange: coalesced copy of `rows` rows from y_local to dst[0..n_dst) (peer
 // addresses, or one NVSwitch multicast address) with `grid` CTAs.
 cudaError_t launch_push_rows(int value_bytes, const void *y_local, void *const *dst, int n_dst, int multicast,
-                             long long rows, int grid, cudaStream_t stream);
+                             long long rows, int grid, int threads, cudaStream_t stream);
 
 // y_local[rows[i]] -> the same element of every destination, i < n <= MAX_CHUNKS (the rows that cross row-block
 // boundaries, final only after the boundary pass).

@@ -97,6 +97,7 @@ struct csr5b200_sharded_s {
     int parity = 0, last = 0;    // buffer the next step writes / the last step wrote
     int transport = CSR5B200_TRANSPORT_AUTO, chunks = 0, push_ctas = 0, barrier = CSR5B200_BARRIER_AUTO, timeout_ms = 0;
     bool shared_device = false, have_matrix = false, csr5 = false;
+    double row_weight = 0.0;     // shards balance nnz + row_weight * rows
     std::vector<Shard> sh;
     std::vector<long long> bounds;
     Workers *workers = nullptr;
@@ -240,7 +241,19 @@ int csr5b200_sharded_input_csr_host(csr5b200_sharded_t s, int m, int n, int nnz,
     // (format_cuda.h:31-41 / utils_cuda.h:25-53 applied to shard boundaries)
     s->bounds.assign(G + 1, 0);
     for (int g = 1; g < G; g++) {
-        long long b = (long long)count_le_host(row_ptr, m + 1, (long long)nnz * g / G) - 1;
+        long long b;
+        if (s->row_weight > 0.0) {
+            // last row r with row_ptr[r] + w * r <= g / G of the total weight (the weight is increasing in r)
+            const double target = ((double)nnz + s->row_weight * m) * g / G;
+            long long lo = 0, hi = (long long)m + 1;
+            while (lo < hi) {
+                const long long mid = lo + ((hi - lo) >> 1);
+                if ((double)row_ptr[mid] + s->row_weight * (double)mid <= target) lo = mid + 1; else hi = mid;
+            }
+            b = lo - 1;
+        } else {
+            b = (long long)count_le_host(row_ptr, m + 1, (long long)nnz * g / G) - 1;
+        }
         if (b < s->bounds[g - 1]) b = s->bounds[g - 1];
         if (b > m) b = m;
         s->bounds[g] = b;
@@ -278,6 +291,13 @@ int csr5b200_sharded_input_csr_host(csr5b200_sharded_t s, int m, int n, int nnz,
     if (!err) s->have_matrix = true;
     s->parity = s->last = 0;
     return err;
+}
+
+int csr5b200_sharded_set_partition(csr5b200_sharded_t s, double row_weight)
+{
+    if (!s || !(row_weight >= 0.0)) return CSR5B200_INVALID_ARGUMENT;
+    s->row_weight = row_weight;
+    return CSR5B200_SUCCESS;
 }
 
 int csr5b200_sharded_set_sigma(csr5b200_sharded_t s, int sigma)

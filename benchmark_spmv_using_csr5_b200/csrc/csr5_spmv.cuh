@@ -704,7 +704,7 @@ template <typename VT> __device__ __forceinline__ void push_store1(const PushArg
     }
 }
 
-constexpr int PUSH_THREADS = 256;
+constexpr int PUSH_THREADS = 1024;   // upper bound; the launch picks the block size (csr5b200_exchange.push_threads)
 
 template <typename VT>
 __global__ void __launch_bounds__(PUSH_THREADS) push_rows_kernel(const PushArgs<VT> a)
@@ -989,7 +989,7 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
         pa.n_dst = n_dst;
         pa.multicast = a.dst_multicast;
         pa.m = pl.m;
-        push_rows_kernel<VT><<<tn.num_sms * 4, PUSH_THREADS, 0, stream>>>(pa);
+        push_rows_kernel<VT><<<tn.num_sms * 4, 256, 0, stream>>>(pa);
         ++*launches;
     }
     return cudaGetLastError();
@@ -1015,8 +1015,11 @@ cudaError_t launch_push_row_list_t(const VT *y_local, VT *const *dst, int n_dst,
 // of the overlapped exchange.  `grid` CTAs only -- it shares the GPU with the SpMV of the next row block.
 template <typename VT>
 cudaError_t launch_push_t(const VT *y_local, VT *const *dst, int n_dst, int multicast, long long rows, int grid,
-                          cudaStream_t stream)
+                          int threads, cudaStream_t stream)
 {
+    if (threads <= 0) threads = 256;
+    if (threads > PUSH_THREADS) threads = PUSH_THREADS;
+    threads = (threads + 31) / 32 * 32;
     if (rows <= 0) return cudaSuccess;
     PushArgs<VT> pa;
     pa.y_local = y_local;
@@ -1024,7 +1027,7 @@ cudaError_t launch_push_t(const VT *y_local, VT *const *dst, int n_dst, int mult
     pa.n_dst = n_dst;
     pa.multicast = multicast;
     pa.m = (int)rows;
-    push_rows_kernel<VT><<<grid, PUSH_THREADS, 0, stream>>>(pa);
+    push_rows_kernel<VT><<<grid, threads, 0, stream>>>(pa);
     return cudaGetLastError();
 }
 

@@ -8,10 +8,10 @@ cudaError_t launch_spmv_part_f32(const Plan &pl, const SpmvTuning &tn, float alp
     return launch_spmv_part_t<float>(pl, tn, alpha, beta, y, sh, call, stream, used, launches);
 }
 cudaError_t launch_push_rows_f32(const void *y_local, void *const *dst, int n_dst, int multicast, long long rows,
-                                 int grid, cudaStream_t stream)
+                                 int grid, int threads, cudaStream_t stream)
 {
     return launch_push_t<float>(static_cast<const float *>(y_local), reinterpret_cast<float *const *>(dst), n_dst, multicast,
-                             rows, grid, stream);
+                             rows, grid, threads, stream);
 }
 cudaError_t launch_push_row_list_f32(const void *y_local, void *const *dst, int n_dst, int multicast, const int *rows,
                                      int n, cudaStream_t stream)

@@ -39,13 +39,19 @@ MAX_SCATTER = 8  # CSR5B200_MAX_SCATTER
 # ---------------------------------------------------------------------------------------------
 # host logic (device-agnostic; exercised on CPU with gloo in tests/test_sharded_cpu.py)
 # ---------------------------------------------------------------------------------------------
-def row_partition(row_ptr, parts: int) -> np.ndarray:
+def row_partition(row_ptr, parts: int, row_weight: float = 0.0) -> np.ndarray:
     """Boundaries r_0 = 0 <= r_1 <= ... <= r_G = m of G contiguous row ranges with balanced nnz:
     r_g = (number of rows r in [0, m] with row_ptr[r] <= g * nnz / G) - 1, i.e. the row that holds nnz
     index g*nnz/G, the LAST such row on ties (the rule of format_cuda.h:31-41 / utils_cuda.h:25-53).
-    ``row_ptr`` may be a numpy array or a torch tensor (any device)."""
+    ``row_ptr`` may be a numpy array or a torch tensor (any device).
+
+    ``row_weight`` > 0 balances nnz + row_weight * rows instead: a shard's SpMV costs its non-zeros, its share of
+    the y exchange costs its rows, and a power-law matrix split by nnz alone leaves the last shard with nearly half
+    of all rows (R-MAT 25 on 8 GPUs: 14.6 M of 33.5 M)."""
     if parts < 1:
         raise ValueError("parts must be >= 1")
+    if row_weight > 0:
+        return _row_partition_weighted(row_ptr, parts, float(row_weight))
     try:
         import torch
         is_t = isinstance(row_ptr, torch.Tensor)
@@ -61,6 +67,25 @@ def row_partition(row_ptr, parts: int) -> np.ndarray:
     else:
         b = np.searchsorted(np.asarray(row_ptr), np.asarray(targets, dtype=np.asarray(row_ptr).dtype),
                             side="right").astype(np.int64) - 1
+    b[0], b[-1] = 0, m
+    return np.maximum.accumulate(np.clip(b, 0, m))
+
+
+def _row_partition_weighted(row_ptr, parts: int, lam: float) -> np.ndarray:
+    try:
+        import torch
+        is_t = isinstance(row_ptr, torch.Tensor)
+    except ImportError:  # pragma: no cover
+        is_t = False
+    m = int(row_ptr.shape[0]) - 1
+    if is_t:
+        import torch
+        w = row_ptr.double() + lam * torch.arange(m + 1, device=row_ptr.device, dtype=torch.float64)
+        t = torch.tensor([g * float(w[-1]) / parts for g in range(parts + 1)], device=row_ptr.device, dtype=torch.float64)
+        b = (torch.searchsorted(w, t, right=True) - 1).cpu().numpy().astype(np.int64)
+    else:
+        w = np.asarray(row_ptr, np.float64) + lam * np.arange(m + 1, dtype=np.float64)
+        b = np.searchsorted(w, [g * w[-1] / parts for g in range(parts + 1)], side="right").astype(np.int64) - 1
     b[0], b[-1] = 0, m
     return np.maximum.accumulate(np.clip(b, 0, m))
 
@@ -104,7 +129,8 @@ class ShardedCsr5:
 
     def __init__(self, bounds, n: int, local_row_ptr, col, val, group=None, mode: str = "overlap",
                  sigma: int = -1, multicast: bool | None = None, scheme: int = 0, transport: str | int = "auto",
-                 chunks: int = 0, push_ctas: int = 0, timeout_ms: int = 0, sigma_rule: int = 0):
+                 chunks: int = 0, push_ctas: int = 0, timeout_ms: int = 0, sigma_rule: int = 0,
+                 push_threads: int = 0):
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -135,6 +161,7 @@ class ShardedCsr5:
         self.scheme = int(scheme)   # fused mode: 0 auto, 1 stores fused into the SpMV kernels, 2 coalesced push pass
         self.transport = H.TRANSPORT_NAMES[transport] if isinstance(transport, str) else int(transport)
         self.chunks, self.push_ctas, self.timeout_ms = int(chunks), int(push_ctas), int(timeout_ms)
+        self.push_threads = int(push_threads)
         self._resolved = False
         self._symm = None
         self._dst = None
@@ -222,6 +249,7 @@ class ShardedCsr5:
         if self.mode == "overlap":
             ex = self._ex[self._parity]
             ex.transport, ex.chunks, ex.push_ctas, ex.timeout_ms = self.transport, self.chunks, self.push_ctas, self.timeout_ms
+            ex.push_threads = self.push_threads
             if beta != 0.0 and self._parity != self._last_parity():
                 # beta * y refers to the y of the previous step, which lives in the other buffer
                 prev_full, prev_local = self._views(self._last_parity())
@@ -313,6 +341,10 @@ class ShardedCsr5Native:
         self.m, self.n = int(m), int(n)
         self._check(self._lib.csr5b200_sharded_input_csr_host(self._s, self.m, self.n, int(ci.size), rp.ctypes.data,
                                                               ci.ctypes.data, v.ctypes.data))
+
+    def set_partition(self, row_weight=0.0):
+        """Before inputCSR: shards balance nnz + row_weight * rows (row_partition's rule)."""
+        self._check(self._lib.csr5b200_sharded_set_partition(self._s, float(row_weight)))
 
     def setSigma(self, sigma=-1):
         self._check(self._lib.csr5b200_sharded_set_sigma(self._s, int(sigma)))

@@ -150,6 +150,7 @@ typedef struct csr5b200_exchange {
     int entry_barrier;                      /* 1 = hold remote writes until all ranks reached this call */
     int push_ctas;                          /* SM transports: CTAs of the push grid (0 = default 48) */
     int timeout_ms;                         /* barrier time-out (0 = default 20000) */
+    int push_threads;                       /* SM transports: threads per CTA of the push grid (0 = default 256, at most 1024) */
 } csr5b200_exchange;
 
 /* y_full[rank][row_begin + i] = alpha * (A_shard x)_i + beta * (old value), i < m, delivered to every rank as

@@ -88,3 +88,25 @@ def test_sharded_allgather_gloo(tmp_path, world, case_idx):
     mp.spawn(_worker, args=(world, port, case_idx, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"r{r}").read() == "ok"
+
+
+def test_row_partition_with_row_weight():
+    """nnz + w * rows balancing: w = 0 is the nnz rule; w > 0 moves rows away from the shards that hold the short rows."""
+    from benchmark_spmv_using_csr5_b200 import matrices as M
+    from benchmark_spmv_using_csr5_b200 import sharded as S
+    import numpy as np
+    A = M.rmat(14)
+    b0 = S.row_partition(A.row_ptr, 4)
+    assert np.array_equal(b0, S.row_partition(A.row_ptr, 4, row_weight=0.0))
+    b8 = S.row_partition(A.row_ptr, 4, row_weight=8.0)
+    assert b8[0] == 0 and b8[-1] == A.m and np.all(np.diff(b8) >= 0)
+    rows0, rows8 = np.diff(b0), np.diff(b8)
+    assert rows8.max() < rows0.max()                                   # the row-heaviest shard shrinks
+    w = A.row_ptr.astype(np.float64) + 8.0 * np.arange(A.m + 1)
+    parts = np.diff(w[b8])
+    assert parts.max() - parts.min() <= 2 * (np.diff(A.row_ptr).max() + 8.0)   # balanced up to one row
+    try:
+        import torch
+        assert np.array_equal(S.row_partition(torch.from_numpy(A.row_ptr), 4, row_weight=8.0), b8)
+    except ImportError:
+        pass

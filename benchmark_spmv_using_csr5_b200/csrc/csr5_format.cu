@@ -323,6 +323,14 @@ desc_offset_kernel(const int *__restrict__ row_ptr, const uint32_t *__restrict__
 // In-place transpose of one omega x sigma tile of col and val per CTA.  CSR order keeps a lane's
 // sigma elements contiguous (lane * sigma + i); CSR5 order is i * 32 + lane.  A tile is skipped
 // when the RAW words tile_ptr[t] == tile_ptr[t+1] (format_cuda.h:540).
+//
+// Replaces aosoa_transpose_kernel_smem (format_cuda.h:525-585: two launches, 29 sigma instantiations): one launch moves
+// col and val together, sigma is a run-time value.  Every warp access is one fully coalesced 128- / 256-byte row and
+// every shared-memory access is conflict-free (odd row stride).  Measured on B200 (profiles/r02_transpose_variants.txt):
+// C2 0.61 ms = 6.3 TB/s (0.96 of the copy peak), C4 2.59 ms = 5.4 TB/s (0.83).  Two re-designs were measured and
+// dropped: 16-byte vector global accesses with a multiply-high instead of the division (C4 2.66 ms: the scalar
+// shared-memory side becomes 2-way conflicted), and the same with four tiles per 256-thread CTA (C4 2.93 ms,
+// C2 0.70 ms).
 template <typename VT>
 __global__ void __launch_bounds__(128)
 transpose_kernel(int *__restrict__ col, VT *__restrict__ val, const uint32_t *__restrict__ tile_ptr,

@@ -545,3 +545,36 @@ def test_deterministic_carry_pass(torch_cuda, oracle):
             assert np.array_equal(_spmv(torch, h2, A.m, tdt), oracle.csr_spmv(A.m, A.row_ptr, A.col, vali, xi)), name
             h.free()
             h2.free()
+
+
+def test_unaligned_caller_arrays(torch_cuda, oracle):
+    """col / val that are only element-aligned (views one element into a buffer): the 16-byte vector transpose and the
+    bulk-TMA kernels need 16-byte alignment and must step aside for their scalar / direct-load forms."""
+    torch = torch_cuda
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    for name in ("example_c1_auto", "two_packet_s26_empty", "banded16_s16"):
+        _n, A, sigma = [c for c in CASES if c[0] == name][0]
+        for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+            val, x = M.values(A.nnz, A.n, "int", dt)
+            big_c = torch.zeros(A.nnz + 1, device="cuda", dtype=torch.int32)
+            big_v = torch.zeros(A.nnz + 1, device="cuda", dtype=tdt)
+            ci, v = big_c[1:], big_v[1:]
+            ci.copy_(torch.from_numpy(A.col))
+            v.copy_(torch.from_numpy(val))
+            assert ci.data_ptr() % 16 != 0
+            rp, xd = torch.from_numpy(A.row_ptr).cuda(), torch.from_numpy(x).cuda()
+            for kernel in (1, 2):
+                h = H.anonymouslibHandle(A.m, A.n, tdt)
+                assert h.inputCSR(A.nnz, rp, ci, v) == 0 and h.setX(xd) == 0
+                h.setSigma(sigma)
+                h.set_option(H.OPT_KERNEL, kernel)
+                assert h.asCSR5() == 0
+                s = h.info().sigma
+                want = oracle.csr5_meta(A.m, A.nnz, s, A.row_ptr)
+                assert np.array_equal(ci.cpu().numpy(), oracle.transpose(A.col, s, A.nnz, want.tile_ptr, True)), name
+                assert np.array_equal(v.cpu().numpy(), oracle.transpose(val, s, A.nnz, want.tile_ptr, True)), name
+                y = _spmv(torch, h, A.m, tdt)
+                assert np.array_equal(y, oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)), name
+                assert h.destroy() == 0
+                assert np.array_equal(ci.cpu().numpy(), A.col) and np.array_equal(v.cpu().numpy(), val)
+                h.free()

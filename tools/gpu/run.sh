@@ -64,6 +64,21 @@ for stage in "$@"; do
       ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | gzip > ${rep}_source.csv.gz
       [ "${KEEP_REP:-0}" == "1" ] || rm -f $rep.ncu-rep
       ls -la ${rep}*; head -12 $rep.md ;;
+    tma)
+      # closing A/B of the TMA-staged kernel with x prefetch against the direct-load kernel: ring-geometry sweep
+      wl=${rest:-c2}
+      : > gpurun_out/${TAG}_tma_sweep_${wl}.txt
+      run1() { timeout 600 python bench.py --workload $wl --no-cpu-baseline --no-e2e --no-extra --steps 60 --sigma-rule 0 "$@" 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('%-40s %-28s kernel_ms %.4f (min %.4f) frac %.3f  GFLOPS %.1f' % ('$*', r['kernel'], r['kernel_ms_avg'], r['kernel_ms_min'], r['frac'], d['value']))
+" | tee -a gpurun_out/${TAG}_tma_sweep_${wl}.txt; }
+      run1 --kernel 1
+      for st in 2 3 4; do for w in 8 11 16; do run1 --kernel 4 --stages $st --warps $w --ctas-per-sm 1; done; done
+      run1 --kernel 4 --stages 2 --warps 8 --ctas-per-sm 2
+      run1 --kernel 4 --stages 3 --warps 5 --ctas-per-sm 2
+      run1 --kernel 2 --stages 3 --warps 11 --ctas-per-sm 1
+      run1 --kernel 1 ;;
     ab)
       # A/B of two builds of the library on the same box, interleaved: ab:<other .so>:<bench args>
       other=${rest%%:*}; a=${rest#*:}; [ "$a" == "$rest" ] && a=""

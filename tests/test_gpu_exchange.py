@@ -262,3 +262,52 @@ def test_native_sharded_argument_errors(torch_cuda):
     assert lib.csr5b200_sharded_spmv(s, 1.0, 0.0) == -101          # no matrix yet
     assert lib.csr5b200_sharded_set_exchange(s, 3, 0, 0, 0, 0) == -101   # multicast: multi-process binding only
     assert lib.csr5b200_sharded_destroy(s) == 0
+
+
+@pytest.mark.parametrize("transport", [1, 2, 4])   # copy engine, push grid, in-kernel stores
+def test_cpp_example_of_the_sharded_host_api(tmp_path, transport):
+    """examples/sharded_spmv.cpp: the sharded SpMV driven from plain C++ (g++, no CUDA headers, no Python) through
+    include/csr5_b200_sharded.h -- three shards on device 0, every shard's gathered y checked against the scalar loop."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not found")
+    from benchmark_spmv_using_csr5_b200 import _lib
+    exe = str(tmp_path / "sharded_spmv")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "sharded_spmv.cpp"), "-L", libdir, "-lcsr5_b200",
+                        f"-Wl,-rpath,{libdir}", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, "3", "200000", "5", str(transport), "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Check... PASS!" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("scheme", [1, 2], ids=["fused", "push"])
+@pytest.mark.parametrize("name,A,sigma", CASES, ids=IDS)
+def test_legacy_scatter_two_local_destinations(torch_cuda, oracle, name, A, sigma, scheme):
+    """csr5b200_spmv_scatter (the first-generation exchange, still shipped as transport IN_KERNEL / for A/B): the MULTI
+    instantiations of the SpMV kernels with two destination buffers on the same GPU standing in for two GPUs."""
+    import ctypes as C
+    from benchmark_spmv_using_csr5_b200 import handle as H
+    torch = torch_cuda
+    if A.nnz == 0:
+        pytest.skip("empty matrix")
+    for dt, tdt in ((np.float64, torch.float64), (np.float32, torch.float32)):
+        val, x = M.values(A.nnz, A.n, "int", dt)
+        y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+        h, _keep = _handle(torch, A, val, x, sigma)
+        assert h.set_option(H.OPT_EXCHANGE, scheme) == 0
+        y_local = torch.full((A.m,), float("nan"), device="cuda", dtype=tdt)
+        y_peer = torch.full((A.m,), float("nan"), device="cuda", dtype=tdt)
+        dst = (C.c_void_p * 2)(y_local.data_ptr(), y_peer.data_ptr())
+        for _ in range(2):
+            assert h.spmv_scatter(1.0, y_local, dst, 2, False) == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(y_local.cpu().numpy(), y_ref), f"{name}: local"
+        assert np.array_equal(y_peer.cpu().numpy(), y_ref), f"{name}: peer"
+        if scheme == 1 and A.m > 0:   # fused: the destination list must contain y_local (carries complete there)
+            only_peer = (C.c_void_p * 1)(y_peer.data_ptr())
+            assert h.spmv_scatter(1.0, y_local, only_peer, 1, False) == -101
+        h.free()

@@ -734,7 +734,7 @@ int csr5b200_call_anonymouslib(int m, int n, int nnz, const int *row_ptr_host, c
     return cleanup(CSR5B200_SUCCESS);
 }
 
-const char *csr5b200_version(void) { return "csr5-b200 0.1 (sm_100a)"; }
+const char *csr5b200_version(void) { return "csr5-b200 0.2 (sm_100a)"; }
 
 const char *csr5b200_error_string(int code)
 {

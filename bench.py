@@ -46,7 +46,7 @@ WORKLOADS = {
     "c4": "27-pt Laplacian 320^3, FP32 (BASELINE.json configs[3])",
     "c5": "R-MAT scale 25, edge factor 16, FP64, row-range sharded by balanced nnz (BASELINE.json configs[4])",
 }
-ROW_WEIGHT = [8.0]   # --row-weight: strong-scaling workloads balance nnz + w * rows per shard instead of nnz alone
+ROW_WEIGHT = [8.0]   # --row-cost: strong-scaling workloads minimise max(nnz, cost * rows) per shard instead of balancing nnz alone
 STRONG = {"c3", "c5"}   # fixed matrix split over the ranks (strong scaling); c2 grows with N (weak)
 
 
@@ -187,7 +187,7 @@ def build_workload(name, torch, device, rank, world):
         n = rp.numel() - 1
         dtype = torch.float64
         val, x = M.device_values(ci.numel(), n, "real", dtype, device, seed=42)
-        bounds = S.row_partition(rp, world, row_weight=ROW_WEIGHT[0])
+        bounds = S.row_partition(rp, world, row_cost=ROW_WEIGHT[0])
         if world > 1:
             lrp, lci, lval = S.shard_csr(rp, ci, val, int(bounds[rank]), int(bounds[rank + 1]))
             lrp, lci, lval = lrp.contiguous(), lci.clone(), lval.clone()
@@ -851,8 +851,8 @@ def main_multi(args, torch, H, device, rank, world, local_rank):
             c5 = {"workload": WORKLOADS["c5"], "ms_1gpu": ms1, "roofline_frac_1gpu": frac1, "ms_N": c5r["ms_step"],
                   "speedup": ms1 / c5r["ms_step"], "gflops_N": c5r["gflops"], "nnz": c5r["total_nnz"],
                   "ms_N_spmv_only_no_exchange": c5r["ms_local"], "exchange": c5r["multi"]["exchange"],
-                  "partition": f"contiguous row ranges balancing nnz + {args.row_weight:g} * rows per shard "
-                               "(a shard's SpMV costs its non-zeros, its share of the y exchange its rows)",
+                  "partition": f"contiguous row ranges minimising max(nnz, {args.row_cost:g} * rows) per shard "
+                               "(a shard's SpMV costs its non-zeros, its share of the overlapped y exchange its rows)",
                   "rows_per_shard": [int(b - a) for a, b in zip(c5r["bounds"][:-1], c5r["bounds"][1:])],
                   "ms_N_spmv_then_nccl_allgather": c5r["multi"]["ms_per_step_spmv_then_nccl_allgather"],
                   "parity_max_rel_err": c5r["max_rel"], "parity": "pass (every rank's gathered y, element-wise)",
@@ -895,7 +895,7 @@ def main_multi(args, torch, H, device, rank, world, local_rank):
             "parity_max_rel_err_vs_fp64_segment_sums": r["max_rel"],
             "parity": "every rank's gathered y compared element-wise with the all-gathered per-rank FP64 references",
             "rows_per_shard": [int(b - a) for a, b in zip(r["bounds"][:-1], r["bounds"][1:])],
-            "partition_row_weight": args.row_weight if args.workload in STRONG else None,
+            "partition_row_cost": args.row_cost if args.workload in STRONG else None,
         },
         "clocks": sampler.summary(windows),
         "e2e": r["e2e"],
@@ -933,10 +933,10 @@ def main():
     ap.add_argument("--push-ctas", type=int, default=0, help="overlap, SM transports: CTAs of the push grid (0 = default)")
     ap.add_argument("--sweep-exchange", default="", help="overlap: also time these variants, e.g. 'ce/8+push/8/32+multicast/8/32' (transport/chunks/push CTAs)")
     ap.add_argument("--push-threads", type=int, default=0, help="overlap, SM transports: threads per CTA of the push grid")
-    ap.add_argument("--row-weight", type=float, default=8.0,
-                    help="strong-scaling workloads (c3 / c5 on N > 1 GPUs): shards balance nnz + w * rows; 0 = nnz alone.  Measured "
-                         "on 8 B200 with R-MAT 25 (profiles/r02_bench_c5_n8_rowweight*.json): w = 0 / 2 / 4 / 6 / 8 -> 0.70-0.74 / 0.68 / "
-                         "0.62 / 0.60 / 0.58 ms per step")
+    ap.add_argument("--row-cost", type=float, default=8.0,
+                    help="strong-scaling workloads (c3 / c5 on N > 1 GPUs): shards minimise max(nnz, cost * rows); 0 = balance "
+                         "nnz alone.  8 bytes of y per row at the ~0.25 TB/s one GPU's multicast stream sustains against 12 "
+                         "bytes per non-zero at half the HBM rate: a row costs about 8 non-zeros (DESIGN.md s6)")
     ap.add_argument("--trace-exchange", action="store_true", help="overlap: per-row-block timeline of one step on every rank")
     ap.add_argument("--scheme", type=int, default=0, help="fused modes: 0 auto, 1 in-kernel stores, 2 push pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -946,7 +946,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true")
     args = ap.parse_args()
     capture_stdout()
-    ROW_WEIGHT[0] = args.row_weight
+    ROW_WEIGHT[0] = args.row_cost
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)

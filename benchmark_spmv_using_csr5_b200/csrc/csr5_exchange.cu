@@ -252,13 +252,16 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
     int transport = ex->transport;
     if (transport < 0 || transport > CSR5B200_TRANSPORT_NONE) return CSR5B200_INVALID_ARGUMENT;
     if (transport == CSR5B200_TRANSPORT_AUTO) {
-        // measured on 2 and 8 B200 (profiles/r02_bench_c2_n2_sweep*.json, ..._n8_sweep*.json): from 3 GPUs up the
-        // NVSwitch multicast address wins by a wide margin (one store per row instead of N - 1, whatever the rows
-        // per shard), without it the push grid; between 2 GPUs the copy engine, or -- for matrices whose tiles
-        // store runs of consecutive rows -- the SpMV kernel's own peer stores
-        const bool consecutive = !pl.needs_zero_fill && pl.m > 0 && (long long)pl.nnz / pl.m <= 64;
-        if (world >= 3) transport = ex->y_multicast ? CSR5B200_TRANSPORT_SM_MULTICAST : CSR5B200_TRANSPORT_SM_PUSH;
-        else transport = (consecutive && beta == 0.0) ? CSR5B200_TRANSPORT_IN_KERNEL : CSR5B200_TRANSPORT_COPY_ENGINE;
+        // measured on 2, 4 and 8 B200 (profiles/r02_bench_c2_n{2,4,8}_sweep*.json).  Matrices whose tiles store runs
+        // of consecutive rows (no empty rows, short rows): up to 4 GPUs the SpMV kernel's own peer stores win (C2:
+        // 0.337 / 0.509 ms at 2 / 4 GPUs against 0.430 / 0.554 through the multicast address), from 5 up the NVSwitch
+        // multicast address (8 GPUs: 0.966 against 1.210) -- one store per row instead of N - 1.  Everything else
+        // (scattered row stores, shards with very different row counts): multicast from 3 GPUs up (push grid without
+        // a multicast address), the copy engine between 2.
+        const bool consecutive = !pl.needs_zero_fill && pl.m > 0 && (long long)pl.nnz / pl.m <= 64 && beta == 0.0;
+        if (consecutive && world <= 4) transport = CSR5B200_TRANSPORT_IN_KERNEL;
+        else if (world >= 3) transport = ex->y_multicast ? CSR5B200_TRANSPORT_SM_MULTICAST : CSR5B200_TRANSPORT_SM_PUSH;
+        else transport = CSR5B200_TRANSPORT_COPY_ENGINE;
     }
     if (transport == CSR5B200_TRANSPORT_SM_MULTICAST && !ex->y_multicast) return CSR5B200_INVALID_ARGUMENT;
     if (world == 1) transport = CSR5B200_TRANSPORT_NONE;

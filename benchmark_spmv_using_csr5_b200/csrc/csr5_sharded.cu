@@ -97,7 +97,7 @@ struct csr5b200_sharded_s {
     int parity = 0, last = 0;    // buffer the next step writes / the last step wrote
     int transport = CSR5B200_TRANSPORT_AUTO, chunks = 0, push_ctas = 0, barrier = CSR5B200_BARRIER_AUTO, timeout_ms = 0;
     bool shared_device = false, have_matrix = false, csr5 = false;
-    double row_weight = 0.0;     // shards balance nnz + row_weight * rows
+    double row_cost = 0.0;       // > 0: shards minimise max(nnz, row_cost * rows) instead of balancing nnz
     std::vector<Shard> sh;
     std::vector<long long> bounds;
     Workers *workers = nullptr;
@@ -240,23 +240,38 @@ int csr5b200_sharded_input_csr_host(csr5b200_sharded_t s, int m, int n, int nnz,
     // shard g starts at the row that holds nnz index g * nnz / G, the LAST such row on ties
     // (format_cuda.h:31-41 / utils_cuda.h:25-53 applied to shard boundaries)
     s->bounds.assign(G + 1, 0);
-    for (int g = 1; g < G; g++) {
-        long long b;
-        if (s->row_weight > 0.0) {
-            // last row r with row_ptr[r] + w * r <= g / G of the total weight (the weight is increasing in r)
-            const double target = ((double)nnz + s->row_weight * m) * g / G;
-            long long lo = 0, hi = (long long)m + 1;
-            while (lo < hi) {
-                const long long mid = lo + ((hi - lo) >> 1);
-                if ((double)row_ptr[mid] + s->row_weight * (double)mid <= target) lo = mid + 1; else hi = mid;
+    if (s->row_cost > 0.0) {
+        // minimise max over shards of max(nnz, row_cost * rows): smallest T for which a left-to-right sweep that closes
+        // a range as late as both limits allow covers all rows with G ranges (the rule of sharded.row_partition)
+        const double rc = s->row_cost;
+        auto sweep = [&](long long T, std::vector<long long> *out) {
+            long long r = 0;
+            const long long max_rows = (long long)((double)T / rc);
+            for (int g = 0; g < G; g++) {
+                if (r < m) {
+                    long long r1 = (long long)count_le_host(row_ptr, m + 1, (long long)row_ptr[r] + T) - 1;
+                    if (r1 > r + max_rows) r1 = r + max_rows;
+                    if (r1 > m) r1 = m;
+                    if (r1 <= r) return false;   // one row alone exceeds T
+                    r = r1;
+                }
+                if (out) (*out)[g + 1] = r;
             }
-            b = lo - 1;
-        } else {
-            b = (long long)count_le_host(row_ptr, m + 1, (long long)nnz * g / G) - 1;
+            return r >= m;
+        };
+        long long lo = 1, hi = (long long)((double)nnz + rc * m) + 1;
+        while (lo < hi) {
+            const long long mid = lo + (hi - lo) / 2;
+            if (sweep(mid, nullptr)) hi = mid; else lo = mid + 1;
         }
-        if (b < s->bounds[g - 1]) b = s->bounds[g - 1];
-        if (b > m) b = m;
-        s->bounds[g] = b;
+        sweep(lo, &s->bounds);
+    } else {
+        for (int g = 1; g < G; g++) {
+            long long b = (long long)count_le_host(row_ptr, m + 1, (long long)nnz * g / G) - 1;
+            if (b < s->bounds[g - 1]) b = s->bounds[g - 1];
+            if (b > m) b = m;
+            s->bounds[g] = b;
+        }
     }
     s->bounds[G] = m;
     s->stride = ((size_t)m + 31) / 32 * 32;
@@ -293,10 +308,10 @@ int csr5b200_sharded_input_csr_host(csr5b200_sharded_t s, int m, int n, int nnz,
     return err;
 }
 
-int csr5b200_sharded_set_partition(csr5b200_sharded_t s, double row_weight)
+int csr5b200_sharded_set_partition(csr5b200_sharded_t s, double row_cost)
 {
-    if (!s || !(row_weight >= 0.0)) return CSR5B200_INVALID_ARGUMENT;
-    s->row_weight = row_weight;
+    if (!s || !(row_cost >= 0.0)) return CSR5B200_INVALID_ARGUMENT;
+    s->row_cost = row_cost;
     return CSR5B200_SUCCESS;
 }
 

@@ -39,19 +39,21 @@ MAX_SCATTER = 8  # CSR5B200_MAX_SCATTER
 # ---------------------------------------------------------------------------------------------
 # host logic (device-agnostic; exercised on CPU with gloo in tests/test_sharded_cpu.py)
 # ---------------------------------------------------------------------------------------------
-def row_partition(row_ptr, parts: int, row_weight: float = 0.0) -> np.ndarray:
+def row_partition(row_ptr, parts: int, row_cost: float = 0.0) -> np.ndarray:
     """Boundaries r_0 = 0 <= r_1 <= ... <= r_G = m of G contiguous row ranges with balanced nnz:
     r_g = (number of rows r in [0, m] with row_ptr[r] <= g * nnz / G) - 1, i.e. the row that holds nnz
     index g*nnz/G, the LAST such row on ties (the rule of format_cuda.h:31-41 / utils_cuda.h:25-53).
     ``row_ptr`` may be a numpy array or a torch tensor (any device).
 
-    ``row_weight`` > 0 balances nnz + row_weight * rows instead: a shard's SpMV costs its non-zeros, its share of
-    the y exchange costs its rows, and a power-law matrix split by nnz alone leaves the last shard with nearly half
-    of all rows (R-MAT 25 on 8 GPUs: 14.6 M of 33.5 M)."""
+    ``row_cost`` > 0: a shard's SpMV costs its non-zeros, its share of the y exchange -- which runs WHILE the SpMV
+    runs -- costs its rows, ``row_cost`` non-zeros' worth each.  The ranges then minimise
+    max over shards of max(nnz, row_cost * rows): the nnz rule wherever rows are not the bottleneck (few GPUs), fewer
+    rows for the shards that hold the short and empty rows of a power-law matrix otherwise (R-MAT 25 on 8 GPUs by nnz
+    alone: the last shard owns 14.6 M of the 33.5 M rows, and one GPU's multicast stream is what the step waits for)."""
     if parts < 1:
         raise ValueError("parts must be >= 1")
-    if row_weight > 0:
-        return _row_partition_weighted(row_ptr, parts, float(row_weight))
+    if row_cost > 0:
+        return _row_partition_minimax(row_ptr, parts, float(row_cost))
     try:
         import torch
         is_t = isinstance(row_ptr, torch.Tensor)
@@ -71,23 +73,43 @@ def row_partition(row_ptr, parts: int, row_weight: float = 0.0) -> np.ndarray:
     return np.maximum.accumulate(np.clip(b, 0, m))
 
 
-def _row_partition_weighted(row_ptr, parts: int, lam: float) -> np.ndarray:
+def _row_partition_minimax(row_ptr, parts: int, row_cost: float) -> np.ndarray:
+    """Smallest T for which a left-to-right sweep that closes a range as late as nnz <= T and row_cost * rows <= T
+    allow covers all rows with `parts` ranges (binary search on T; the sweep is `parts` binary searches)."""
     try:
         import torch
-        is_t = isinstance(row_ptr, torch.Tensor)
+        if isinstance(row_ptr, torch.Tensor):
+            row_ptr = row_ptr.detach().cpu().numpy()
     except ImportError:  # pragma: no cover
-        is_t = False
-    m = int(row_ptr.shape[0]) - 1
-    if is_t:
-        import torch
-        w = row_ptr.double() + lam * torch.arange(m + 1, device=row_ptr.device, dtype=torch.float64)
-        t = torch.tensor([g * float(w[-1]) / parts for g in range(parts + 1)], device=row_ptr.device, dtype=torch.float64)
-        b = (torch.searchsorted(w, t, right=True) - 1).cpu().numpy().astype(np.int64)
-    else:
-        w = np.asarray(row_ptr, np.float64) + lam * np.arange(m + 1, dtype=np.float64)
-        b = np.searchsorted(w, [g * w[-1] / parts for g in range(parts + 1)], side="right").astype(np.int64) - 1
-    b[0], b[-1] = 0, m
-    return np.maximum.accumulate(np.clip(b, 0, m))
+        pass
+    rp = np.asarray(row_ptr, np.int64)
+    m = rp.shape[0] - 1
+    nnz = int(rp[-1])
+
+    def sweep(T):
+        b, r = [0], 0
+        max_rows = int(T // row_cost)
+        for _ in range(parts):
+            if r >= m:
+                b.append(m)
+                continue
+            r1 = int(np.searchsorted(rp, rp[r] + T, side="right")) - 1   # last boundary with nnz <= T
+            r1 = min(r1, r + max_rows, m)
+            if r1 <= r:
+                return None                                             # one row alone exceeds T
+            b.append(r1)
+            r = r1
+        return b if r >= m else None
+
+    lo, hi = 1, int(nnz + row_cost * m) + 1
+    while lo < hi:
+        mid = (lo + hi) // 2
+        if sweep(mid) is not None:
+            hi = mid
+        else:
+            lo = mid + 1
+    b = sweep(lo)
+    return np.asarray(b, np.int64)
 
 
 def shard_csr(row_ptr, col, val, row_begin: int, row_end: int):
@@ -342,9 +364,9 @@ class ShardedCsr5Native:
         self._check(self._lib.csr5b200_sharded_input_csr_host(self._s, self.m, self.n, int(ci.size), rp.ctypes.data,
                                                               ci.ctypes.data, v.ctypes.data))
 
-    def set_partition(self, row_weight=0.0):
-        """Before inputCSR: shards balance nnz + row_weight * rows (row_partition's rule)."""
-        self._check(self._lib.csr5b200_sharded_set_partition(self._s, float(row_weight)))
+    def set_partition(self, row_cost=0.0):
+        """Before inputCSR: shards minimise max(nnz, row_cost * rows) (row_partition's rule)."""
+        self._check(self._lib.csr5b200_sharded_set_partition(self._s, float(row_cost)))
 
     def setSigma(self, sigma=-1):
         self._check(self._lib.csr5b200_sharded_set_sigma(self._s, int(sigma)))

@@ -46,11 +46,13 @@ CSR5B200_API int csr5b200_sharded_create(int n_shards, const int *devices, int v
  * balanced nnz and upload each row range to its device.  The host arrays are not kept. */
 CSR5B200_API int csr5b200_sharded_input_csr_host(csr5b200_sharded_t s, int m, int n, int nnz, const int *row_ptr,
                                                  const int *col, const void *val);
-/* Before input_csr_host: shards balance nnz + row_weight * rows instead of nnz alone (default 0).  A shard's SpMV
- * costs its non-zeros, its share of the y exchange costs its rows; a power-law matrix split by nnz alone leaves the
- * last shard with nearly half of all rows (R-MAT 25 on 8 GPUs: 14.6 M of 33.5 M rows; 0.70 -> 0.58 ms per step with
- * row_weight 8, profiles/r02_bench_c5_n8_rowweight*.json). */
-CSR5B200_API int csr5b200_sharded_set_partition(csr5b200_sharded_t s, double row_weight);
+/* Before input_csr_host: with row_cost > 0 the row ranges minimise max over shards of max(nnz, row_cost * rows)
+ * instead of balancing nnz alone (default 0).  A shard's SpMV costs its non-zeros; its share of the y exchange, which
+ * runs while the SpMV runs, costs its rows -- row_cost non-zeros' worth each (8 on B200: 8 bytes at the ~0.25 TB/s one
+ * GPU's multicast stream sustains against 12 bytes per non-zero at half the HBM rate).  Where rows are not the
+ * bottleneck this is the nnz rule; a power-law matrix on many GPUs sheds rows from the shard that holds the short and
+ * empty ones (R-MAT 25 on 8 GPUs by nnz alone: 14.6 M of 33.5 M rows in the last shard; 0.70 -> 0.58 ms per step). */
+CSR5B200_API int csr5b200_sharded_set_partition(csr5b200_sharded_t s, double row_cost);
 /* sigma for every shard (CSR5B200_AUTO_TUNED_SIGMA: each shard applies the rule to its own nnz / m). */
 CSR5B200_API int csr5b200_sharded_set_sigma(csr5b200_sharded_t s, int sigma);
 /* csr5b200_set_option on every shard's handle. */

@@ -311,3 +311,24 @@ def test_legacy_scatter_two_local_destinations(torch_cuda, oracle, name, A, sigm
             only_peer = (C.c_void_p * 1)(y_peer.data_ptr())
             assert h.spmv_scatter(1.0, y_local, only_peer, 1, False) == -101
         h.free()
+
+
+def test_native_partition_by_row_cost_matches_python_rule(torch_cuda, oracle):
+    """csr5b200_sharded_set_partition: the C++ host applies the same max(nnz, cost * rows) rule as sharded.row_partition,
+    and the result stays exact whatever the partition."""
+    from benchmark_spmv_using_csr5_b200 import sharded as S
+    A = M.rmat(13)
+    val, x = M.values(A.nnz, A.n, "int", np.float64)
+    y_ref = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)
+    for cost in (0.0, 3.0, 8.0):
+        sh = S.ShardedCsr5Native([0, 0, 0, 0], np.float64)
+        sh.set_partition(cost)
+        sh.inputCSR(A.m, A.n, A.row_ptr, A.col, val)
+        assert np.array_equal(sh.bounds(), S.row_partition(A.row_ptr, 4, row_cost=cost)), cost
+        sh.set_exchange("push", chunks=4, push_ctas=4, barrier=S.BARRIER_EVENTS, timeout_ms=5000)
+        sh.setX(x)
+        sh.asCSR5()
+        sh.spmv(1.0)
+        for g in range(4):
+            assert np.array_equal(sh.y(g), y_ref), (cost, g)
+        sh.destroy()

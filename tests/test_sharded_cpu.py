@@ -90,23 +90,29 @@ def test_sharded_allgather_gloo(tmp_path, world, case_idx):
         assert open(tmp_path / f"r{r}").read() == "ok"
 
 
-def test_row_partition_with_row_weight():
-    """nnz + w * rows balancing: w = 0 is the nnz rule; w > 0 moves rows away from the shards that hold the short rows."""
+def test_row_partition_with_row_cost():
+    """max(nnz, cost * rows) minimisation: the nnz rule where rows do not bind, fewer rows for the row-heavy shard where
+    they do; never worse than the nnz rule under its own objective."""
     from benchmark_spmv_using_csr5_b200 import matrices as M
     from benchmark_spmv_using_csr5_b200 import sharded as S
     import numpy as np
     A = M.rmat(14)
-    b0 = S.row_partition(A.row_ptr, 4)
-    assert np.array_equal(b0, S.row_partition(A.row_ptr, 4, row_weight=0.0))
-    b8 = S.row_partition(A.row_ptr, 4, row_weight=8.0)
-    assert b8[0] == 0 and b8[-1] == A.m and np.all(np.diff(b8) >= 0)
-    rows0, rows8 = np.diff(b0), np.diff(b8)
-    assert rows8.max() < rows0.max()                                   # the row-heaviest shard shrinks
-    w = A.row_ptr.astype(np.float64) + 8.0 * np.arange(A.m + 1)
-    parts = np.diff(w[b8])
-    assert parts.max() - parts.min() <= 2 * (np.diff(A.row_ptr).max() + 8.0)   # balanced up to one row
+
+    def objective(b, cost):
+        return max(np.diff(A.row_ptr[b].astype(np.int64)).max(), cost * np.diff(b).max())
+
+    for parts in (2, 4, 8):
+        b0 = S.row_partition(A.row_ptr, parts)
+        assert np.array_equal(b0, S.row_partition(A.row_ptr, parts, row_cost=0.0))
+        b = S.row_partition(A.row_ptr, parts, row_cost=7.0)
+        assert len(b) == parts + 1 and b[0] == 0 and b[-1] == A.m and np.all(np.diff(b) >= 0)
+        assert objective(b, 7.0) <= objective(b0, 7.0)
+    b0, b8 = S.row_partition(A.row_ptr, 8), S.row_partition(A.row_ptr, 8, row_cost=7.0)
+    assert np.diff(b8).max() < np.diff(b0).max()            # the row-heaviest shard sheds rows at 8 shards
     try:
         import torch
-        assert np.array_equal(S.row_partition(torch.from_numpy(A.row_ptr), 4, row_weight=8.0), b8)
+        assert np.array_equal(S.row_partition(torch.from_numpy(A.row_ptr), 8, row_cost=7.0), b8)
     except ImportError:
         pass
+    B = M.banded(10000, 16)                                 # uniform rows: the nnz rule either way
+    assert np.array_equal(S.row_partition(B.row_ptr, 4, row_cost=7.0), S.row_partition(B.row_ptr, 4))

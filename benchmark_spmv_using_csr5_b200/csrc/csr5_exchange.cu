@@ -279,16 +279,17 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
     if (pl.m <= 0 || pl.p == 0) {   // nothing to compute: clear / scale the rows, then only the barriers
         SpmvCall all;
         CUX(spmv_part(h, alpha, beta, y_local, nullptr, all, S));
+        if (barriers && ex->entry_barrier) {
+            CUX(launch_flag_barrier(ex->flags, rank, world, 0, x.epoch, x.status, ex->timeout_ms, S));
+            ++h->launches_per_spmv;
+        }
+        // a shard of empty rows only: its (cleared / scaled) rows still have to reach every peer
+        if (pl.m > 0 && transport != CSR5B200_TRANSPORT_NONE)
+            for (int k = 0; k < world; k++)
+                if (k != rank)
+                    CUX(cudaMemcpyAsync(static_cast<char *>(ex->y_full[k]) + (size_t)ex->row_begin * vb, y_local,
+                                        (size_t)pl.m * vb, cudaMemcpyDefault, S));
         if (barriers) {
-            if (ex->entry_barrier) {
-                CUX(launch_flag_barrier(ex->flags, rank, world, 0, x.epoch, x.status, ex->timeout_ms, S));
-                ++h->launches_per_spmv;
-            }
-            if (pl.m > 0 && transport != CSR5B200_TRANSPORT_NONE)
-                for (int k = 0; k < world; k++)
-                    if (k != rank)
-                        CUX(cudaMemcpyAsync(static_cast<char *>(ex->y_full[k]) + (size_t)ex->row_begin * vb, y_local,
-                                            (size_t)pl.m * vb, cudaMemcpyDefault, S));
             CUX(launch_flag_barrier(ex->flags, rank, world, 1, x.epoch, x.status, ex->timeout_ms, S));
             ++h->launches_per_spmv;
         }

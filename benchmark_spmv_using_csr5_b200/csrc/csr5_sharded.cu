@@ -451,6 +451,20 @@ int csr5b200_sharded_iterate(csr5b200_sharded_t s, int steps, double alpha)
             if (err) break;
         }
     }
+    if (!err && steps > 0) {
+        // leave x in the shards' own x buffers: the y buffer it lives in is rewritten by the step after next
+        const size_t bytes = (size_t)s->n * s->vb;
+        for (auto &x : s->sh) {
+            if (cudaSetDevice(x.dev) != cudaSuccess) { err = CSR5B200_CUDA_ERROR; break; }
+            cudaError_t e = cudaSuccess;
+            if (!x.x) e = cudaMalloc(&x.x, bytes ? bytes : 1);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(x.x, static_cast<char *>(x.ybuf) + (size_t)s->last * s->stride * s->vb, bytes,
+                                    cudaMemcpyDeviceToDevice, x.stream);
+            if (e != cudaSuccess) { err = cu(s, e); break; }
+            if ((err = csr5b200_set_x(x.h, x.x))) break;
+        }
+    }
     cudaSetDevice(dev);
     return err;
 }

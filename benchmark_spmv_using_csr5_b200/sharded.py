@@ -316,6 +316,12 @@ class ShardedCsr5:
             err = self.h.setX(y)
             if err:
                 raise RuntimeError(self.h.error_string(err))
+        if y is not None and self.mode == "overlap":
+            # leave x in a tensor of its own: the y buffer it lives in is rewritten by the step after next
+            self._x_keep = y.clone()
+            err = self.h.setX(self._x_keep)
+            if err:
+                raise RuntimeError(self.h.error_string(err))
         return y
 
     def exchange_status(self) -> int:

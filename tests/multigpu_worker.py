@@ -79,6 +79,12 @@ def main():
         torch.cuda.synchronize()
         if sh.exchange_status() != 0 or not np.array_equal(y.cpu().numpy(), want):
             bad.append(("iterate", mode, tr))
+        want4 = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, want)
+        for _ in range(3):   # x = the last iterate, in a buffer of its own: further steps must not overwrite it
+            y = sh.spmv(1.0)
+            torch.cuda.synchronize()
+            if not np.array_equal(y.cpu().numpy(), want4):
+                bad.append(("iterate+spmv", mode, tr))
         dist.barrier()
         sh.free()
     print(f"rank {rank}: {'OK' if not bad else 'MISMATCH ' + str(bad)}", flush=True)

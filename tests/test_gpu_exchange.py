@@ -178,6 +178,12 @@ def test_native_sharded_iterate_feeds_y_back_as_x(torch_cuda, oracle):
         sh.iterate(3)
         for g in range(3):
             assert np.array_equal(sh.y(g), want), transport
+        # x is now the last iterate, held in a buffer of its own: further steps must not eat it
+        want4 = oracle.csr_spmv(A.m, A.row_ptr, A.col, val, want)
+        for _ in range(3):
+            sh.spmv(1.0)
+            for g in range(3):
+                assert np.array_equal(sh.y(g), want4), transport
         sh.destroy()
 
 

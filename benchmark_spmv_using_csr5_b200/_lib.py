@@ -34,7 +34,7 @@ class Csr5Info(C.Structure):
         ("last_cuda_error", C.c_int), ("launches_per_spmv", C.c_int),
         ("hot_columns", C.c_int), ("hot_coverage", C.c_double),
         ("convert_phase_ms", C.c_float * 8), ("convert_host_ms", C.c_double), ("convert_alloc_ms", C.c_double),
-        ("exchange_transport", C.c_int), ("exchange_chunks", C.c_int),
+        ("exchange_transport", C.c_int), ("exchange_chunks", C.c_int), ("has_carries", C.c_int),
     ]
 
 

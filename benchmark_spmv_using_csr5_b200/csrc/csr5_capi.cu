@@ -337,6 +337,7 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
     pl.tail_start = 0;
     pl.num_offsets = 0;
     pl.needs_zero_fill = 0;
+    pl.has_carries = 1;
 
     if (pl.p == 0) {  // empty matrix: spmv() only clears y
         h->format = CSR5B200_FORMAT_CSR5;
@@ -385,12 +386,15 @@ int csr5b200_as_csr5(csr5b200_handle_t h)
     // One blocking read-back (the reference does three, anonymouslib_cuda.h:166, format_cuda.h:331,342):
     // tail start, first tile's row, number of empty-row table entries, "any dirty tile" flag.
     uint32_t tp_last = 0, tp_first = 0;
-    int num_offsets = 0, any_dirty = 0;
+    int num_offsets = 0, any_dirty = 0, any_carry = 1;
     CUF(cudaMemcpyAsync(&tp_last, pl.tile_ptr + pl.p - 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CUF(cudaMemcpyAsync(&tp_first, pl.tile_ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CUF(cudaMemcpyAsync(&num_offsets, pl.desc_off_ptr + pl.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUF(cudaMemcpyAsync(&any_dirty, pl.dev_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUF(cudaMemcpyAsync(&any_carry, pl.dev_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CUF(cudaStreamSynchronize(h->stream));
+    // no tile continues a row (e.g. 16 nnz/row at sigma 16): spmv() skips the carry pass, one launch per SpMV
+    pl.has_carries = any_carry ? 1 : 0;
     pl.tail_start = (int)(tp_last & ROW_MASK);
     pl.num_offsets = num_offsets;
     // Rows that no tile stores: empty rows inside CSR5 tiles and the empty rows in front of the
@@ -587,6 +591,7 @@ int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out)
     out->convert_alloc_ms = h->convert_alloc_ms;
     out->exchange_transport = h->ex.last_transport;
     out->exchange_chunks = h->ex.last_chunks;
+    out->has_carries = pl.has_carries;
     return CSR5B200_SUCCESS;
 }
 

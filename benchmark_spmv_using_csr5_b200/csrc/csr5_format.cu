@@ -89,7 +89,10 @@ tile_desc_kernel(const int *__restrict__ row_ptr, uint32_t *tile_ptr, uint32_t *
         // One row covers the whole tile (fast track).  The only row start that can fall inside is
         // one exactly on the tile boundary; the reference keeps that raw flag (format_cuda.h:187).
         uint32_t w0 = 0;
-        if (lane == 0 && (long long)row_ptr[start] == base) w0 = 1u << (31 - bit_all);
+        if (lane == 0) {
+            if ((long long)row_ptr[start] == base) w0 = 1u << (31 - bit_all);
+            else if (t > 0) dev_flags[1] = 1;   // the tile continues a row: some SpMV carry exists
+        }
         td[lane] = w0;
         if (num_packet > 1) td[OMEGA + lane] = 0;
         return;
@@ -162,6 +165,7 @@ tile_desc_kernel(const int *__restrict__ row_ptr, uint32_t *tile_ptr, uint32_t *
     td[lane] = (uint32_t)(word >> 32);
     if (num_packet > 1) td[OMEGA + lane] = (uint32_t)word;
 
+    if (lane == 0 && t > 0 && !(f & 1u)) dev_flags[1] = 1;   // first element is not a row start (tail tile included)
     if (lane == 0 && dirty) {
         tile_ptr[t] = start | MSB;
         if (t < p - 1) {

@@ -26,6 +26,7 @@ struct Plan {
     int tail_start = 0;
     int num_offsets = 0;
     int needs_zero_fill = 0;
+    int has_carries = 1;    // 0: every tile (and the tail) starts on a row boundary -- the carry pass has nothing to add
 
     const int *row_ptr = nullptr;   // borrowed
     int *col = nullptr;             // borrowed, permuted in place while in CSR5 format
@@ -37,7 +38,7 @@ struct Plan {
     int *desc_off_ptr = nullptr;    // owned, p + 1
     int *desc_off = nullptr;        // owned, num_offsets
     void *calibrator = nullptr;     // owned, p values
-    int *dev_flags = nullptr;       // owned, small scratch: [0] any dirty tile before the tail
+    int *dev_flags = nullptr;       // owned, small scratch: [0] any dirty tile before the tail, [1] any tile that continues a row
 
     // Hot-column table (no reference counterpart).  While hot_k > 0 the column indices
     // of the hot_k most referenced columns are stored in the CSR5 tiles as (bit 31 | slot); asCSR()

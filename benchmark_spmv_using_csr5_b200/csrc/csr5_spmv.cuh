@@ -919,7 +919,7 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
     a.tail_warps = tail ? (pl.m - pl.tail_start + 31) / 32 : 0;
     const int threads = 256;
     if (call.boundary) {
-        if (pl.p > 0) {
+        if (pl.p > 0 && pl.has_carries) {
             calibrate_boundary_kernel<VT><<<(pl.p + threads - 1) / threads, threads, 0, stream>>>(a, *call.boundary);
             ++*launches;
         }
@@ -968,7 +968,7 @@ cudaError_t launch_spmv_part_t(const Plan &pl, const SpmvTuning &tn, VT alpha, V
         if (tn.ev_end && (e = cudaEventRecord(tn.ev_end, stream)) != cudaSuccess) return e;
         ++*launches;
     }
-    if (call.calibrate && pl.p > 0) {
+    if (call.calibrate && pl.p > 0 && pl.has_carries) {   // nothing to add when every tile starts on a row boundary
         const int cb = a.tile_begin, ce = tail ? pl.p : a.tile_end;   // the tail tile's carry is calibrator[p - 1]
         if (ce > cb) {
             if (tn.deterministic)

@@ -228,6 +228,7 @@ typedef struct csr5b200_info {
     double convert_alloc_ms;   /* of which buffer (re)allocation; 0 when the handle's buffer pool already fits */
     int exchange_transport;    /* csr5b200_spmv_allgather: transport and row blocks of the last step */
     int exchange_chunks;
+    int has_carries;           /* 0: every tile starts on a row boundary, spmv() is ONE launch (no carry pass) */
 } csr5b200_info;
 CSR5B200_API int csr5b200_get_info(csr5b200_handle_t h, csr5b200_info *out);
 

@@ -578,3 +578,20 @@ def test_unaligned_caller_arrays(torch_cuda, oracle):
                 assert h.destroy() == 0
                 assert np.array_equal(ci.cpu().numpy(), A.col) and np.array_equal(v.cpu().numpy(), val)
                 h.free()
+
+
+def test_carry_pass_is_skipped_when_no_tile_continues_a_row(torch_cuda, oracle):
+    """16 nnz/row at sigma 16 (the headline configuration): every tile and the tail start on a row boundary, so spmv() is
+    one launch; any matrix with a row crossing a tile boundary keeps the carry pass."""
+    torch = torch_cuda
+    for name, want_carries in (("banded16_s16", 0), ("rows_eq_tile_s4", 0), ("banded16_exact_multiple", 0),
+                               ("hub_row_s12", 1), ("random_noempty_s8", 1), ("example_c1_auto", 1)):
+        _n, A, sigma = [c for c in CASES if c[0] == name][0]
+        val, x = M.values(A.nnz, A.n, "int")
+        h, _keep = _handle(torch, A, val, x, sigma, kernel=1)
+        y = _spmv(torch, h, A.m, torch.float64)
+        i = h.info()
+        assert i.has_carries == want_carries, name
+        assert i.launches_per_spmv == (1 if not want_carries else 2) + (1 if i.needs_zero_fill else 0), name
+        assert np.array_equal(y, oracle.csr_spmv(A.m, A.row_ptr, A.col, val, x)), name
+        h.free()

@@ -127,3 +127,41 @@ def test_cpp_shim_compiles_standalone(tmp_path):
                         os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_round2_entry_points_reject_bad_arguments_without_a_gpu():
+    """Host-side argument checks of the entry points added in round 2 (no compute call is made)."""
+    lib = _lib.load_library()
+    h = C.c_void_p()
+    assert lib.csr5b200_create(3, 3, 8, C.byref(h)) == 0
+    # y = alpha A x + beta y / the sharded step before inputCSR / asCSR5: the reference's format codes
+    assert lib.csr5b200_spmv_axpby(h, 1.0, 1.0, C.c_void_p(16)) == -1            # ANONYMOUSLIB_UNKOWN_FORMAT
+    ex = _lib.Csr5Exchange()
+    ex.rank, ex.world = 0, 1
+    assert lib.csr5b200_spmv_allgather(h, 1.0, 0.0, C.byref(ex)) == -1
+    assert lib.csr5b200_spmv_allgather(None, 1.0, 0.0, C.byref(ex)) == -101
+    assert lib.csr5b200_spmv_allgather(h, 1.0, 0.0, None) == -101
+    assert lib.csr5b200_input_csr(h, 0, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16)) == 0
+    assert lib.csr5b200_spmv_axpby(h, 1.0, 1.0, C.c_void_p(16)) == -4            # spmv on CSR: asCSR5 first
+    assert lib.csr5b200_spmv_allgather(h, 1.0, 0.0, C.byref(ex)) == -4
+    for opt, bad in ((12, 2), (12, -1), (11, 3), (1, 3)):                          # sigma rule / exchange / kernel ids
+        assert lib.csr5b200_set_option(h, opt, bad) == -101
+    for opt in (12, 13, 14):                                                       # sigma rule, deterministic, trace
+        assert lib.csr5b200_set_option(h, opt, 1) == 0
+    ms, cnt = (C.c_float * 4)(), C.c_int(7)
+    assert lib.csr5b200_exchange_trace(h, ms, 4, C.byref(cnt)) == 0 and cnt.value == 0
+    assert lib.csr5b200_probe(h, 1, 0, ms) == -101 and lib.csr5b200_probe(h, 1, 1, ms) == -4
+    assert lib.csr5b200_free(h) == 0
+    # COO -> CSR
+    n_out = C.c_int(0)
+    assert lib.csr5b200_coo_to_csr(-1, 1, 0, None, None, None, 8, 0, C.c_void_p(16), None, None, 0, C.byref(n_out), None) == -101
+    assert lib.csr5b200_coo_to_csr(1, 1, 1, None, None, None, 8, 0, C.c_void_p(16), None, None, 0, C.byref(n_out), None) == -101
+    assert lib.csr5b200_coo_to_csr(1, 1, 0, None, None, None, 2, 0, C.c_void_p(16), None, None, 0, C.byref(n_out), None) == -5
+    # sharded host API
+    s = C.c_void_p()
+    assert lib.csr5b200_sharded_create(0, (C.c_int * 1)(0), 8, C.byref(s)) == -101
+    assert lib.csr5b200_sharded_create(9, (C.c_int * 9)(*([0] * 9)), 8, C.byref(s)) == -101
+    assert lib.csr5b200_sharded_create(1, (C.c_int * 1)(0), 3, C.byref(s)) == -5
+    assert lib.csr5b200_sharded_spmv(None, 1.0, 0.0) == -101
+    assert lib.csr5b200_sharded_destroy(None) == 0
+    assert b"timed out" in lib.csr5b200_error_string(-102)

@@ -64,6 +64,14 @@ for stage in "$@"; do
       ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | gzip > ${rep}_source.csv.gz
       [ "${KEEP_REP:-0}" == "1" ] || rm -f $rep.ncu-rep
       ls -la ${rep}*; head -12 $rep.md ;;
+    cppsharded)
+      # the C++ host API on real peers: examples/sharded_spmv.cpp with one shard per visible GPU (or <rest> shards)
+      g++ -O2 -std=c++17 -Iinclude examples/sharded_spmv.cpp -Lbenchmark_spmv_using_csr5_b200 -lcsr5_b200 \
+          -Wl,-rpath,$PWD/benchmark_spmv_using_csr5_b200 -o /tmp/sharded_spmv || echo "compile failed"
+      n=${rest:-$(nvidia-smi -L | wc -l)}
+      for tr in 0 1 2 4; do
+        timeout 300 /tmp/sharded_spmv $n 10000000 30 $tr 0 2>&1 | tail -3 | sed "s/^/[transport $tr] /" | tee -a gpurun_out/${TAG}_cppsharded_n${n}.txt
+      done ;;
     tma)
       # closing A/B of the TMA-staged kernel with x prefetch against the direct-load kernel: ring-geometry sweep
       wl=${rest:-c2}

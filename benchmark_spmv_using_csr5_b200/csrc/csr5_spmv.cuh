@@ -563,6 +563,9 @@ hot_gather_kernel(const VT *__restrict__ x, const int *__restrict__ hot_col, VT 
 
 constexpr int HOT_MAX_THREADS = 1024;
 
+// (Measured and dropped, profiles/r02_probe_hot_two_ctas.txt: two 640-thread CTAs per SM with a table copy each -- 40
+// resident warps at 48 registers instead of 32 at 64 -- is slower, C3 0.237 vs 0.226 ms with 8 K entries and 0.325 ms
+// with 12 K: what the second table takes from L1 costs more than the extra warps bring.)
 template <typename VT, int SIGMA, bool MULTI, int NCH = 0>
 __global__ void __launch_bounds__(HOT_MAX_THREADS, 1)
 spmv_hot_kernel(const SpmvArgs<VT> a, const VT *__restrict__ hot_x, const uint32_t hot_bytes)

@@ -48,6 +48,7 @@ void release_csr5_arrays(csr5b200_handle_t h)
     pl.calibrator = nullptr;
     pl.dev_flags = nullptr;
     h->ex.chunks = 0;   // row-block boundaries of the exchange belong to the released tile_ptr
+    h->ex.auto_chunks = 0;
     h->ex.chunk_tile.clear();
     h->ex.chunk_row.clear();
 }

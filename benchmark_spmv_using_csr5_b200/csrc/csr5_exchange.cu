@@ -210,7 +210,8 @@ int ensure_chunks(csr5b200_handle_t h, int chunks)
     auto rows_of = [&](int c) { return (long long)x.chunk_row[c + 1] - x.chunk_row[c]; };
     long long lo = rows_of(0), hi = rows_of(0);
     for (int c = 1; c < chunks; c++) { lo = std::min(lo, rows_of(c)); hi = std::max(hi, rows_of(c)); }
-    if (hi > 2 * lo + 1024)
+    x.reordered = hi > 2 * lo + 1024;
+    if (x.reordered)
         std::stable_sort(x.chunk_order.begin(), x.chunk_order.end(), [&](int a, int b) { return rows_of(a) > rows_of(b); });
     x.chunks = chunks;
     return CSR5B200_SUCCESS;
@@ -298,9 +299,17 @@ int csr5b200_spmv_allgather(csr5b200_handle_t h, double alpha, double beta, cons
         return CSR5B200_SUCCESS;
     }
 
-    int chunks = ex->chunks > 0 ? ex->chunks : 12;
+    // Default block count, measured on 8 GPUs (profiles/r02_bench_c2_n8_sweep2.json, r02_bench_c5_n8_chunks_trace.json):
+    // 12 for shards whose blocks carry similar numbers of rows (C2: 6 / 8 / 12 / 16 blocks -> 0.994 / 0.985 / 0.966 /
+    // 0.965 ms), 8 when they differ so much that the blocks are reordered (R-MAT 25: 4 / 8 / 12 / 16 / 24 blocks ->
+    // 0.581 / 0.575 / 0.591 / 0.609 / 0.668 ms: every block costs a push launch on the critical path).
+    int chunks = ex->chunks > 0 ? ex->chunks : (x.auto_chunks > 0 ? x.auto_chunks : 12);
     if (transport == CSR5B200_TRANSPORT_IN_KERNEL) chunks = 1;
     if ((err = ensure_chunks(h, chunks))) return err;
+    if (ex->chunks <= 0 && x.auto_chunks == 0 && transport != CSR5B200_TRANSPORT_IN_KERNEL) {
+        x.auto_chunks = x.reordered ? 8 : 12;
+        if (x.auto_chunks != x.chunks && (err = ensure_chunks(h, x.auto_chunks))) return err;
+    }
     chunks = x.chunks;
     const int push_ctas = ex->push_ctas > 0 ? ex->push_ctas : 48;
 

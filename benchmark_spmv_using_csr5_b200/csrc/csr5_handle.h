@@ -21,6 +21,8 @@ struct ExchangeState {
     cudaEvent_t ev_chunk[MAX_CHUNKS] = {}, ev_cal[MAX_CHUNKS] = {};
     cudaEvent_t ev_ce_done[CSR5B200_MAX_SCATTER] = {};
     int chunks = 0;                                     // row blocks the cached boundaries are for
+    int auto_chunks = 0;                                // what `chunks = 0` resolved to for this matrix (0 = not yet)
+    bool reordered = false;                             // the blocks run ship-heavy first (very different row counts)
     std::vector<int> chunk_tile, chunk_row;             // chunks + 1 boundaries: tiles, rows
     std::vector<int> chunk_carried;                     // row chunk_row[c] began before block c (boundary row)
     std::vector<int> chunk_order;                       // execution order of the blocks

@@ -145,7 +145,7 @@ typedef struct csr5b200_exchange {
     void *y_multicast;                      /* NVSwitch multicast address of the same buffer, or NULL */
     uint32_t *flags[CSR5B200_MAX_SCATTER];  /* rank k's barrier words (>= 2 * world, zeroed once) as mapped here; NULL = no barriers */
     long long row_begin;                    /* first row of this shard inside the concatenated y */
-    int chunks;                             /* row blocks (0 = default 12, at most 64) */
+    int chunks;                             /* row blocks (0 = default: 12, or 8 for shards whose blocks differ widely in rows; at most 64) */
     int transport;                          /* CSR5B200_TRANSPORT_* */
     int entry_barrier;                      /* 1 = hold remote writes until all ranks reached this call */
     int push_ctas;                          /* SM transports: CTAs of the push grid (0 = default 48) */

@@ -102,7 +102,7 @@ def test_allgather_world1_chunks_bit_identical(torch_cuda, oracle, name, A, sigm
         p = h.info().p
         # carries of multi-tile rows are added with atomics: only rows fed by more than one carry can differ
         # in the last bit between runs, so compare with the documented tolerance and bit-exactly on int data
-        for chunks in (1, 2, 3, 7, 64):
+        for chunks in (0, 1, 2, 3, 7, 64):
             y = torch.full((A.m,), float("nan"), device="cuda", dtype=tdt)
             ex = _lib.Csr5Exchange()
             ex.rank, ex.world = 0, 1

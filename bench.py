@@ -46,7 +46,7 @@ WORKLOADS = {
     "c4": "27-pt Laplacian 320^3, FP32 (BASELINE.json configs[3])",
     "c5": "R-MAT scale 25, edge factor 16, FP64, row-range sharded by balanced nnz (BASELINE.json configs[4])",
 }
-ROW_WEIGHT = [8.0]   # --row-cost: strong-scaling workloads minimise max(nnz, cost * rows) per shard instead of balancing nnz alone
+ROW_COST = [8.0]   # --row-cost: strong-scaling workloads minimise max(nnz, cost * rows) per shard instead of balancing nnz alone
 STRONG = {"c3", "c5"}   # fixed matrix split over the ranks (strong scaling); c2 grows with N (weak)
 
 
@@ -187,7 +187,7 @@ def build_workload(name, torch, device, rank, world):
         n = rp.numel() - 1
         dtype = torch.float64
         val, x = M.device_values(ci.numel(), n, "real", dtype, device, seed=42)
-        bounds = S.row_partition(rp, world, row_cost=ROW_WEIGHT[0])
+        bounds = S.row_partition(rp, world, row_cost=ROW_COST[0])
         if world > 1:
             lrp, lci, lval = S.shard_csr(rp, ci, val, int(bounds[rank]), int(bounds[rank + 1]))
             lrp, lci, lval = lrp.contiguous(), lci.clone(), lval.clone()
@@ -946,7 +946,7 @@ def main():
     ap.add_argument("--no-numa", action="store_true")
     args = ap.parse_args()
     capture_stdout()
-    ROW_WEIGHT[0] = args.row_cost
+    ROW_COST[0] = args.row_cost
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)

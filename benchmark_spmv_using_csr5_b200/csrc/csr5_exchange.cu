@@ -17,7 +17,6 @@
 // block -- and the blocks run ship-heavy first (most rows per tile: a power-law shard keeps its millions of short
 // and empty rows at the end), the order that minimises the makespan of the two-stage compute -> ship pipeline.
 #include <algorithm>
-#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <numeric>

@@ -64,6 +64,15 @@ for stage in "$@"; do
       ncu -i $rep.ncu-rep --page source --csv 2>/dev/null | gzip > ${rep}_source.csv.gz
       [ "${KEEP_REP:-0}" == "1" ] || rm -f $rep.ncu-rep
       ls -la ${rep}*; head -12 $rep.md ;;
+    sanitize)
+      # compute-sanitizer over a small, adversarial subset of the GPU tests (memcheck, then racecheck on the shared-memory kernels)
+      sel='long_empty or huge_span or device_coo_to_csr_matches or (chunks_bit_identical and example_c1) or (axpby and hub_row) or (native_sharded_on_one_gpu and two_packet_s26 and push)'
+      # test_gpu_refcuda.py runs the REFERENCE's own kernels (libref_cuda.so), whose rounded-up grids read out of bounds
+      #  -- memcheck flags them, so they are left out here
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "$sel" \
+          --ignore tests/test_gpu_refcuda.py > gpurun_out/${TAG}_sanitize_memcheck_full.txt 2>&1
+      tail -8 gpurun_out/${TAG}_sanitize_memcheck_full.txt | tee gpurun_out/${TAG}_sanitize_memcheck.txt
+      timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests -m gpu -x -q -k "device_coo_to_csr_matches or (metadata_word_for_word and long_empty)" 2>&1 | tail -8 | tee gpurun_out/${TAG}_sanitize_racecheck.txt ;;
     cppsharded)
       # the C++ host API on real peers: examples/sharded_spmv.cpp with one shard per visible GPU (or <rest> shards)
       g++ -O2 -std=c++17 -Iinclude examples/sharded_spmv.cpp -Lbenchmark_spmv_using_csr5_b200 -lcsr5_b200 \

@@ -26,6 +26,11 @@ Exchange modes:
   previous y) and one after them bracket the step.
 * ``"nccl"``: local SpMV into this rank's slot, then an all-gather(-v) over NCCL (the baseline; also
   what runs on gloo in the CPU tests of the host logic).
+
+The overlap step runs about a dozen streams per GPU and ends in a device-side barrier kernel that spins until the
+peers arrive; export ``CUDA_DEVICE_MAX_CONNECTIONS=32`` before CUDA is initialised (``bench.py`` and the tests do) so
+that every stream has a hardware queue of its own and no kernel is ever queued behind a barrier it does not depend
+on.  The barriers time out (``timeout_ms``, default 20 s; ``exchange_status()``) rather than hang.
 """
 from __future__ import annotations
 

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CSR5B200_LIB: another build of the same library (A/B experiments, e.g. libcsr5_b200_nopark.so from `make PARK=0`)
+# CSR5B200_LIB: another build of the same library for A/B experiments (`make VARIANT=x EXTRA=-D...` -> libcsr5_b200_x.so)
 LIB_PATH = os.path.join(_HERE, os.environ.get("CSR5B200_LIB", "libcsr5_b200.so"))
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "csr5_b200.h")
 HEADER_PATHS = [HEADER_PATH, os.path.join(os.path.dirname(_HERE), "include", "csr5_b200_sharded.h")]
